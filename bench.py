@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the KernelSHAP hot path: instances explained / second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA engine (N > 1: run under torchrun)
+  python bench.py --impl reference [...]                         the reference's CPU path on the host cores
+
+Workload (config[1] of BASELINE.json): Adult-shaped synthetic tabular data (the real pickles need the network),
+D = 49 encoded columns in 12 groups, 100 background rows, 2-class multinomial logistic regression, logit link,
+nsamples = 2048, l1_reg = False; 2560 instances per GPU (weak scaling: every rank explains its own 2560).
+
+A "step" explains the 2560 instances once.  ``value`` times steps with the inputs resident in HBM (CUDA events on
+the engine's stream, L2 flushed between steps); ``e2e`` times the same step through the reference-facing plug-in
+(`KernelShap._explainer.get_explanation`, i.e. the dks_explain_host C-ABI call) from pinned HOST buffers, including
+the H2D copy of X and the D2H copy of the shap values.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_INSTANCES = 2560
+N_BACKGROUND = 100
+NSAMPLES = 2048
+METRIC = "instances explained/sec (bg=100, nsamples=2048)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-oracle timing")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="instances the CPU baseline explains")
+    return ap.parse_args()
+
+
+def workload(rank=0):
+    """Adult-shaped problem; bg/model identical on every rank, the instances differ per rank (seed + rank)."""
+    from distributedkernelshap_b200.datasets import adult_like
+    base = adult_like(n_explain=N_INSTANCES, n_background=N_BACKGROUND, seed=0)
+    if rank > 0:
+        other = adult_like(n_explain=N_INSTANCES, n_background=N_BACKGROUND, seed=1000 + rank)
+        base["X_explain"] = other["X_explain"]
+    return base
+
+
+def config_dict(world, kernel):
+    return {"workload": "Adult-shaped synthetic LR (BASELINE.json configs[1]): 2560 instances/GPU, D=49, 12 groups, "
+                        "bg=100, nsamples=2048, l1_reg=False, logit link",
+            "instances_per_gpu": N_INSTANCES, "global_instances": N_INSTANCES * world, "background": N_BACKGROUND,
+            "nsamples": NSAMPLES, "features": 49, "groups": 12, "plan": "shared per M (seed 0)",
+            "parallelism": f"dp{world} (instances sharded, one all-gather of phi)", "kernel": kernel,
+            "l2_flush_between_steps": True}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Explain a slice of instances with the oracle in a single-threaded worker (one ray actor = one CPU)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    lo, hi = args
+    from oracle.shap_kernel_oracle import DenseData, KernelExplainerWrapperOracle
+    wl = workload()
+    dd = DenseData(wl["background"], wl["group_names"], wl["groups"])
+    expl = KernelExplainerWrapperOracle(wl["predictor"].predict_proba, dd, link="logit", seed=0, faithful_run=True)
+    t0 = time.perf_counter()
+    expl.get_explanation(wl["X_explain"][lo:hi], nsamples=NSAMPLES, l1_reg=False, silent=True)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(sample):
+    """One worker, `sample` instances (== reference `--workers 1`; ~0.6 s per instance)."""
+    t = _cpu_worker((0, sample))
+    return {"value": sample / t, "unit": "instances/s", "cores": 1, "kind": "port",
+            "sample": f"first {sample} of the 2560 instances, oracle/shap_kernel_oracle.py (NumPy restatement of "
+                      f"shap 0.35.0 KernelExplainer, interpreted S x N reduction loop kept), 1 process, {t:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; shap/ray are not installable offline) on all host
+    cores, one single-threaded worker process per core like the ray ActorPool (distributed.py:125)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 2
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            chunks = [(w * per_worker, (w + 1) * per_worker) for w in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, chunks)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    per_step = cores * per_worker
+    ms = 1e3 * sum(times) / len(times)
+    value = per_step / (ms / 1e3)
+    sample = (f"{per_step} instances per step ({per_worker} per worker process x {cores} single-threaded workers) of the "
+              "Adult-shaped workload; oracle port of shap 0.35.0 (faithful interpreted reduction loop)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(1, "cpu-oracle"),
+            "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from distributedkernelshap_b200 import parallel
+    from distributedkernelshap_b200.explainers.kernel_shap import KernelShap
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = workload(rank)
+    X = np.ascontiguousarray(wl["X_explain"], dtype=np.float64)
+    n, D = X.shape
+    # the reference's call sequence (benchmarks/ray_pool.py:34-37); under torchrun distributed_opts selects the SPMD path
+    dopts = {"n_cpus": world, "batch_size": None, "actor_cpu_fraction": 1.0} if world > 1 else None
+    explainer = KernelShap(wl["predictor"].predict_proba, link="logit", feature_names=wl["group_names"], seed=0,
+                           distributed_opts=dopts)
+    explainer.fit(wl["data"]["background"]["X"]["preprocessed"], group_names=wl["group_names"], groups=wl["groups"])
+    plugin = explainer._explainer                       # DistributedExplainer (N > 1) or the engine itself
+    engine = plugin.pool[0] if world > 1 else plugin
+    engine.set_kernel(args.kernel)
+    G, C = engine.data.groups_size, engine.D
+
+    # first call builds + uploads the shared plans (one per M present) -- outside every timed region
+    sv0 = engine.get_explanation(X, nsamples=NSAMPLES, l1_reg=False, silent=True)
+
+    # ---------------- device-resident steps: `value` ----------------
+    stream = torch.cuda.current_stream()
+    engine.set_stream(stream.cuda_stream)
+    X_dev = torch.from_numpy(X).cuda()
+    phi_dev = torch.empty((C, n, G), dtype=torch.float64, device="cuda")
+    phi_all = torch.empty((world, C, n, G), dtype=torch.float64, device="cuda") if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
+
+    def step_device():
+        engine.explain_device(X_dev.data_ptr(), n, phi_dev.data_ptr(), nsamples=NSAMPLES)
+        if world > 1:
+            dist.all_gather_into_tensor(phi_all, phi_dev)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    engine.check_status()
+    launches0 = engine.kernel_launches()
+    kernel_ms = []
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    for k in range(args.steps):
+        flush.zero_()
+        starts[k].record(stream)
+        step_device()
+        ends[k].record(stream)
+        if k % 4 == 3:                       # per-kernel device time of this step (sync happens outside event pairs)
+            kernel_ms.append(engine.last_timings_ms()["coalitions"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    engine.check_status()
+    launches = engine.kernel_launches() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = world * n / (ms_per_step / 1e3)
+    np.testing.assert_allclose(phi_dev[1].cpu().numpy(), sv0[1], rtol=0, atol=1e-12)   # same values as the host path
+
+    # ---------------- end to end through the plug-in with host buffers: `e2e` ----------------
+    X_pin = torch.empty((world * n if world > 1 else n, D), dtype=torch.float64).pin_memory()
+    if world > 1:
+        gathered = [torch.empty((n, D), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, X_dev)
+        X_pin.copy_(torch.cat(gathered).cpu())
+    else:
+        X_pin.copy_(torch.from_numpy(X))
+    X_host = X_pin.numpy()
+    for _ in range(max(2, args.warmup // 2)):
+        plugin.get_explanation(X_host, nsamples=NSAMPLES, l1_reg=False, silent=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = plugin.get_explanation(X_host, nsamples=NSAMPLES, l1_reg=False, silent=True)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(e2e_s.item())
+    h2d = n * D * 8
+    d2h = C * n * G * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (fused coalition kernel) ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = 4.0 * NSAMPLES * N_BACKGROUND * D * n            # B_alg = 4*S*N*D per instance
+    k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_per_step
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    elems = float(NSAMPLES) * N_BACKGROUND * n                   # sigmoid evaluations per launch (T_alg)
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    mufu_peak = 148 * 16 * sm_mhz * 1e6                          # MUFU ops/s at the observed clock
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "explain_" + ("tcgen05" if engine.kernel == "tcgen05" else "simt") + "_kernel",
+                "kernel_ms": k_ms, "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes of the reference-shaped masked batch (4*S*N*D per instance, SURVEY "
+                        "§8d) / kernel time; the fused kernel never materialises that batch, so this is an EFFECTIVE "
+                        "fraction (> 1 is expected). The kernel's real bound is the MUFU pipe: see mufu_frac.",
+                "mufu_ops_per_s": 2 * elems / (k_ms * 1e-3), "mufu_frac": 2 * elems / (k_ms * 1e-3) / mufu_peak}
+
+    line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 sigmoid/accumulate, f64 link + WLS", "data": "synthetic",
+            "config": config_dict(world, engine.kernel),
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "KernelShap._explainer.get_explanation -> dks_explain_host (pinned host X in, host phi out)"},
+            "gpu_launches": int(launches), "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

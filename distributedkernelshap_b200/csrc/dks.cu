@@ -1,0 +1,569 @@
+// libdks.so -- host side of the C ABI declared in include/dks.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "dks_kernels.cuh"
+#include "dks_tc.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(DKS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                  \
+    do {                                                    \
+        if (!(cond)) return fail(DKS_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+    return DKS_OK;
+}
+
+template <typename T>
+void dev_free(T** p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+int bind(dks_ctx* ctx) {
+    if (!ctx) return fail(DKS_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return DKS_OK;
+}
+
+#define BIND(ctx)                      \
+    do {                               \
+        int _rc = bind(ctx);           \
+        if (_rc != DKS_OK) return _rc; \
+    } while (0)
+
+#define TRY(expr)                      \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != DKS_OK) return _rc; \
+    } while (0)
+
+int ensure_workspace(dks_ctx* ctx, int n) {
+    if (n <= ctx->cap_n) return DKS_OK;
+    const int G = ctx->G, R = ctx->R, C = ctx->C;
+    TRY(dev_alloc(&ctx->d_XW, (size_t)n * G * R));
+    TRY(dev_alloc(&ctx->d_vflag, (size_t)n * G));
+    TRY(dev_alloc(&ctx->d_vmask, (size_t)n));
+    TRY(dev_alloc(&ctx->d_M, (size_t)n));
+    TRY(dev_alloc(&ctx->d_dlink, (size_t)n * C));
+    ctx->cap_n = n;
+    return DKS_OK;
+}
+
+int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
+    const int G = ctx->G;
+    TRY(ensure_workspace(ctx, n));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    dks::prep_group_kernel<<<cdiv((long long)n * G, 256), 256, 0, ctx->stream>>>(
+        X_dev, ctx->d_W, ctx->d_bg, ctx->d_goff, ctx->d_gcols, ctx->d_colmin, ctx->d_colmax, ctx->d_colnan, n, ctx->N,
+        ctx->D, G, ctx->R, ctx->d_XW, ctx->d_vflag);
+    dks::prep_instance_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(
+        ctx->d_XW, ctx->d_vflag, ctx->d_b, ctx->d_linkfnull, n, G, ctx->R, ctx->C, ctx->act, ctx->kappa, ctx->link,
+        ctx->d_vmask, ctx->d_M, ctx->d_dlink, ctx->d_hist);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->cur_n = n;
+    ctx->cur_X = X_dev;
+    ctx->prepared = true;
+    return DKS_OK;
+}
+
+int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const double* ext_w, int ext_stride) {
+    REQUIRE(ctx->prepared, "dks_explain: call dks_prepare_* first");
+    REQUIRE((ext_z == nullptr) == (ext_w == nullptr), "ext_zbits and ext_w must both be given or both be NULL");
+    const int n = ctx->cur_n;
+    ExplainParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.N = ctx->N; p.G = ctx->G; p.R = ctx->R; p.C = ctx->C;
+    p.act = ctx->act; p.link = ctx->link; p.S_req = ctx->nsamples_req;
+    p.scale = ctx->scale;
+    p.BWs = ctx->d_BWs; p.bases = ctx->d_bases; p.wbf = ctx->d_wbf; p.wbg = ctx->d_wbg; p.Bbar = ctx->d_Bbar;
+    p.fnull = ctx->d_fnull; p.linkfnull = ctx->d_linkfnull;
+    p.XW = ctx->d_XW; p.vmask = ctx->d_vmask; p.Mcnt = ctx->d_M; p.dlink = ctx->d_dlink;
+    p.plans = ctx->d_plans; p.ext_z = ext_z; p.ext_w = ext_w; p.ext_stride = ext_stride;
+    p.phi = phi_dev; p.status = ctx->d_status;
+    // capacity of the per-CTA y buffer: the largest S any instance can need
+    int S_cap = 0;
+    if (ext_z) S_cap = ext_stride;
+    else S_cap = ctx->max_plan_S;
+    if (S_cap < 2) S_cap = 2;
+    p.S_cap = S_cap;
+
+    int kernel = ctx->kernel_choice;
+    if (kernel == DKS_KERNEL_AUTO) kernel = dks::tc_supported(ctx, p) ? DKS_KERNEL_TCGEN05 : DKS_KERNEL_SIMT;
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (kernel == DKS_KERNEL_TCGEN05) {
+        if (!dks::tc_supported(ctx, p))
+            return fail(DKS_ERR_UNSUPPORTED, "tcgen05 kernel does not support this shape/head (N=%d G=%d act=%d)", ctx->N,
+                        ctx->G, ctx->act);
+        TRY(dks::tc_launch(ctx, p));
+    } else {
+        size_t smem = dks::simt_smem_bytes(S_cap, ctx->N, ctx->G);
+        if ((long long)smem > (long long)ctx->max_smem_optin)
+            return fail(DKS_ERR_UNSUPPORTED, "SIMT kernel needs %zu B of shared memory (> %d): N*G or nsamples too large",
+                        smem, ctx->max_smem_optin);
+        CUDA_TRY(cudaFuncSetAttribute(dks::explain_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)((size_t)ctx->max_smem_optin / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int grid = ctx->sm_count * per_sm;
+        if (grid > n) grid = n;
+        dks::explain_simt_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+        ctx->launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return DKS_OK;
+}
+
+int check_status(dks_ctx* ctx) {
+    // status was copied to h_status by the caller and the stream synchronised
+    if (ctx->h_status[0] == 0) return DKS_OK;
+    if (ctx->h_status[0] == DKS_ERR_PLAN_MISSING)
+        return fail(DKS_ERR_PLAN_MISSING, "no shared plan for M=%d at the current nsamples", ctx->h_status[1]);
+    if (ctx->h_status[0] == DKS_ERR_NUMERIC)
+        return fail(DKS_ERR_NUMERIC, "normal matrix not positive definite (instance/M %d)", ctx->h_status[1]);
+    return fail(ctx->h_status[0], "explain kernel reported status %d (detail %d)", ctx->h_status[0], ctx->h_status[1]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dks_version(void) { return DKS_VERSION; }
+
+const char* dks_last_error(void) { return g_last_error.c_str(); }
+
+int dks_device_count(int* count) {
+    if (!count) return fail(DKS_ERR_INVALID, "dks_device_count: NULL");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *count = c;
+    return DKS_OK;
+}
+
+int dks_create(dks_ctx** out, int device) {
+    if (!out) return fail(DKS_ERR_INVALID, "dks_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(DKS_ERR_CUDA, "dks_create: no CUDA device (%s) -- the engine has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(DKS_ERR_INVALID, "dks_create: device %d out of range [0,%d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(DKS_ERR_UNSUPPORTED, "dks_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    dks_ctx* ctx = new dks_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_plans, sizeof(ctx->h_plans)));
+    CUDA_TRY(cudaMemset(ctx->d_plans, 0, sizeof(ctx->h_plans)));
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_hist, sizeof(int) * (DKS_MAX_GROUPS + 1)));
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_status, sizeof(int) * 2));
+    CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int) * 2));
+    *out = ctx;
+    return DKS_OK;
+}
+
+int dks_destroy(dks_ctx* ctx) {
+    if (!ctx) return DKS_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    dev_free(&ctx->d_bg); dev_free(&ctx->d_wbg); dev_free(&ctx->d_W); dev_free(&ctx->d_b);
+    dev_free(&ctx->d_goff); dev_free(&ctx->d_gcols); dev_free(&ctx->d_colmin); dev_free(&ctx->d_colmax);
+    dev_free(&ctx->d_colnan); dev_free(&ctx->d_BW); dev_free(&ctx->d_scores); dev_free(&ctx->d_Bbar);
+    dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
+    dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW);
+    dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
+    dev_free(&ctx->d_hist); dev_free(&ctx->d_status); dev_free(&ctx->d_phi); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_extw);
+    for (void* p : ctx->plan_allocs) cudaFree(p);
+    dks::tc_release(ctx);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DKS_OK;
+}
+
+int dks_set_stream(dks_ctx* ctx, void* stream) {
+    BIND(ctx);
+    if (ctx->own_stream && ctx->stream) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaStreamDestroy(ctx->stream));
+    }
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+    return DKS_OK;
+}
+
+int dks_synchronize(dks_ctx* ctx) {
+    BIND(ctx);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DKS_OK;
+}
+
+int dks_set_background(dks_ctx* ctx, const double* bg_host, int N, int D, const double* weights_host) {
+    BIND(ctx);
+    REQUIRE(bg_host && N > 0 && D > 0, "dks_set_background: need bg, N > 0, D > 0");
+    ctx->N = N; ctx->D = D;
+    ctx->h_bg.assign(bg_host, bg_host + (size_t)N * D);
+    ctx->h_wbg.assign(N, 1.0 / N);
+    if (weights_host) {
+        double sum = 0;
+        for (int j = 0; j < N; ++j) sum += weights_host[j];
+        REQUIRE(sum > 0, "dks_set_background: weights must have a positive sum");
+        for (int j = 0; j < N; ++j) ctx->h_wbg[j] = weights_host[j] / sum;
+    }
+    ctx->fitted = false;
+    return DKS_OK;
+}
+
+int dks_set_groups(dks_ctx* ctx, const int32_t* group_offsets, const int32_t* group_cols, int G) {
+    BIND(ctx);
+    REQUIRE(group_offsets && group_cols && G > 0, "dks_set_groups: need offsets, cols, G > 0");
+    if (G > DKS_MAX_GROUPS)
+        return fail(DKS_ERR_UNSUPPORTED, "dks_set_groups: G=%d groups; this build handles at most %d (one 64-bit word of "
+                    "coalition bits per row)", G, DKS_MAX_GROUPS);
+    ctx->G = G;
+    ctx->h_goff.assign(group_offsets, group_offsets + G + 1);
+    ctx->h_gcols.assign(group_cols, group_cols + group_offsets[G]);
+    ctx->fitted = false;
+    return DKS_OK;
+}
+
+int dks_set_model(dks_ctx* ctx, const double* W_host, const double* b_host, int R, int activation, double kappa,
+                  int scalar_out) {
+    BIND(ctx);
+    REQUIRE(ctx->D > 0, "dks_set_model: call dks_set_background first (D unknown)");
+    REQUIRE(W_host && b_host && R > 0, "dks_set_model: need W, b, R > 0");
+    if (R > 8) return fail(DKS_ERR_UNSUPPORTED, "dks_set_model: R=%d score rows; at most 8 supported", R);
+    if (activation == DKS_ACT_BINARY_LOGISTIC) {
+        REQUIRE(R == 1, "binary-logistic head needs R == 1 (got %d)", R);
+        REQUIRE(kappa > 0, "binary-logistic head needs kappa > 0");
+        ctx->C = 2;
+    } else if (activation == DKS_ACT_IDENTITY) {
+        ctx->C = R;
+    } else if (activation == DKS_ACT_SOFTMAX) {
+        return fail(DKS_ERR_UNSUPPORTED, "general softmax head (C > 2) is not implemented yet");
+    } else {
+        return fail(DKS_ERR_INVALID, "dks_set_model: unknown activation %d", activation);
+    }
+    ctx->R = R; ctx->act = activation; ctx->kappa = kappa; ctx->scalar_out = scalar_out;
+    ctx->h_W.assign(W_host, W_host + (size_t)R * ctx->D);
+    ctx->h_b.assign(b_host, b_host + R);
+    ctx->fitted = false;
+    return DKS_OK;
+}
+
+int dks_set_link(dks_ctx* ctx, int link) {
+    BIND(ctx);
+    REQUIRE(link == DKS_LINK_IDENTITY || link == DKS_LINK_LOGIT, "dks_set_link: unknown link %d", link);
+    ctx->link = link;
+    ctx->fitted = false;
+    return DKS_OK;
+}
+
+int dks_fit(dks_ctx* ctx) {
+    BIND(ctx);
+    REQUIRE(ctx->N > 0 && ctx->R > 0, "dks_fit: background and model must be set first");
+    const int N = ctx->N, D = ctx->D, R = ctx->R, C = ctx->C;
+    if (ctx->G == 0) {  // default: one singleton group per column (DenseData default)
+        if (D > DKS_MAX_GROUPS)
+            return fail(DKS_ERR_UNSUPPORTED, "D=%d ungrouped columns; this build handles at most %d groups", D, DKS_MAX_GROUPS);
+        ctx->G = D;
+        ctx->h_goff.resize(D + 1);
+        ctx->h_gcols.resize(D);
+        for (int c = 0; c <= D; ++c) ctx->h_goff[c] = c;
+        for (int c = 0; c < D; ++c) ctx->h_gcols[c] = c;
+    }
+    const int G = ctx->G;
+    {   // every column in exactly one group
+        std::vector<int> seen(D, 0);
+        REQUIRE((int)ctx->h_gcols.size() == D, "groups cover %d columns but the data has %d", (int)ctx->h_gcols.size(), D);
+        for (int c : ctx->h_gcols) {
+            REQUIRE(c >= 0 && c < D, "group column %d out of range", c);
+            REQUIRE(seen[c]++ == 0, "column %d appears in more than one group", c);
+        }
+    }
+    TRY(dev_alloc(&ctx->d_bg, (size_t)N * D));
+    TRY(dev_alloc(&ctx->d_wbg, (size_t)N));
+    TRY(dev_alloc(&ctx->d_W, (size_t)R * D));
+    TRY(dev_alloc(&ctx->d_b, (size_t)R));
+    TRY(dev_alloc(&ctx->d_goff, (size_t)G + 1));
+    TRY(dev_alloc(&ctx->d_gcols, (size_t)D));
+    TRY(dev_alloc(&ctx->d_colmin, (size_t)D));
+    TRY(dev_alloc(&ctx->d_colmax, (size_t)D));
+    TRY(dev_alloc(&ctx->d_colnan, (size_t)D));
+    TRY(dev_alloc(&ctx->d_BW, (size_t)N * G * R));
+    TRY(dev_alloc(&ctx->d_scores, (size_t)N * R));
+    TRY(dev_alloc(&ctx->d_Bbar, (size_t)G * R));
+    TRY(dev_alloc(&ctx->d_fnull, (size_t)C));
+    TRY(dev_alloc(&ctx->d_linkfnull, (size_t)C));
+    TRY(dev_alloc(&ctx->d_BWs, (size_t)N * G * R));
+    TRY(dev_alloc(&ctx->d_bases, (size_t)N * R));
+    TRY(dev_alloc(&ctx->d_wbf, (size_t)N));
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_bg, ctx->h_bg.data(), sizeof(double) * N * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_wbg, ctx->h_wbg.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_W, ctx->h_W.data(), sizeof(double) * R * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_b, ctx->h_b.data(), sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_goff, ctx->h_goff.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_gcols, ctx->h_gcols.data(), sizeof(int32_t) * D, cudaMemcpyHostToDevice, st));
+
+    ctx->scale = (ctx->act == DKS_ACT_BINARY_LOGISTIC) ? -ctx->kappa * 1.4426950408889634 : 1.0;
+    dks::fit_bw_kernel<<<cdiv((long long)N * G * R, 256), 256, 0, st>>>(ctx->d_bg, ctx->d_W, ctx->d_goff, ctx->d_gcols, N, D,
+                                                                           G, R, ctx->d_BW);
+    dks::fit_scores_kernel<<<cdiv((long long)N * R, 256), 256, 0, st>>>(ctx->d_BW, ctx->d_b, N, G, R, ctx->d_scores);
+    dks::fit_colstats_kernel<<<cdiv(D, 128), 128, 0, st>>>(ctx->d_bg, N, D, ctx->d_colmin, ctx->d_colmax, ctx->d_colnan);
+    dks::fit_fnull_kernel<<<1, 256, 0, st>>>(ctx->d_scores, ctx->d_BW, ctx->d_wbg, N, G, R, C, ctx->act, ctx->kappa,
+                                              ctx->link, ctx->d_fnull, ctx->d_linkfnull, ctx->d_Bbar);
+    dks::fit_scale_kernel<<<cdiv((long long)N * G * R, 256), 256, 0, st>>>(ctx->d_BW, ctx->d_scores, ctx->d_wbg, N, G, R,
+                                                                              ctx->scale, ctx->d_BWs, ctx->d_bases, ctx->d_wbf);
+    ctx->launches += 5;
+    CUDA_TRY(cudaGetLastError());
+    ctx->h_fnull.resize(C);
+    ctx->h_linkfnull.resize(C);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_fnull.data(), ctx->d_fnull, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_linkfnull.data(), ctx->d_linkfnull, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->cap_n = 0;  // workspace shapes depend on G, R, C
+    ctx->prepared = false;
+    TRY(dks::tc_fit(ctx));
+    ctx->fitted = true;
+    return DKS_OK;
+}
+
+int dks_num_outputs(dks_ctx* ctx, int* C) {
+    BIND(ctx);
+    REQUIRE(C, "dks_num_outputs: NULL");
+    *C = ctx->C;
+    return DKS_OK;
+}
+
+int dks_get_fnull(dks_ctx* ctx, double* fnull_host, double* expected_value_host) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_get_fnull: call dks_fit first");
+    for (int c = 0; c < ctx->C; ++c) {
+        if (fnull_host) fnull_host[c] = ctx->h_fnull[c];
+        if (expected_value_host) expected_value_host[c] = ctx->h_linkfnull[c];
+    }
+    return DKS_OK;
+}
+
+int dks_predict_host(dks_ctx* ctx, const double* X_host, int n, double* out_host) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_predict_host: call dks_fit first");
+    REQUIRE(X_host && out_host && n > 0, "dks_predict_host: bad arguments");
+    double *dX = nullptr, *dO = nullptr;
+    TRY(dev_alloc(&dX, (size_t)n * ctx->D));
+    TRY(dev_alloc(&dO, (size_t)n * ctx->C));
+    CUDA_TRY(cudaMemcpyAsync(dX, X_host, sizeof(double) * n * ctx->D, cudaMemcpyHostToDevice, ctx->stream));
+    dks::predict_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(dX, ctx->d_W, ctx->d_b, n, ctx->D, ctx->R, ctx->C, ctx->act,
+                                                                ctx->kappa, dO);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_host, dO, sizeof(double) * n * ctx->C, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dX); cudaFree(dO);
+    return DKS_OK;
+}
+
+int dks_set_nsamples(dks_ctx* ctx, int nsamples) {
+    BIND(ctx);
+    REQUIRE(nsamples >= 0, "dks_set_nsamples: nsamples must be >= 0 (0 = auto)");
+    ctx->nsamples_req = nsamples;
+    return DKS_OK;
+}
+
+int dks_effective_nsamples(dks_ctx* ctx, int M, int* S) {
+    REQUIRE(ctx && S && M >= 0, "dks_effective_nsamples: bad arguments");
+    *S = dks_effective_S(M, ctx->nsamples_req);
+    return DKS_OK;
+}
+
+int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, const double* w_host) {
+    BIND(ctx);
+    REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_shared_plan: M=%d out of [2,%d]", M, DKS_MAX_GROUPS);
+    REQUIRE(S >= 1 && zbits_host && w_host, "dks_set_shared_plan: bad arguments");
+    uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S));
+    CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S));
+    CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
+    ctx->plan_allocs.push_back(dz); ctx->plan_allocs.push_back(dw); ctx->plan_allocs.push_back(dc);
+    CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
+    size_t smem = sizeof(double) * (size_t)(M - 1) * (M - 1);
+    dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, ctx->d_status);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_status[0] != 0)
+        return fail(DKS_ERR_NUMERIC, "dks_set_shared_plan: normal matrix of the M=%d plan is not positive definite", M);
+    PlanDev pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.z = dz; pd.w = dw; pd.chol = dc; pd.S = S;
+    ctx->h_plans[M] = pd;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (S > ctx->max_plan_S) ctx->max_plan_S = S;
+    TRY(dks::tc_plan_changed(ctx, M));
+    return DKS_OK;
+}
+
+int dks_clear_plans(dks_ctx* ctx) {
+    BIND(ctx);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (void* p : ctx->plan_allocs) cudaFree(p);
+    ctx->plan_allocs.clear();
+    memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+    ctx->max_plan_S = 0;
+    CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
+    return DKS_OK;
+}
+
+int dks_has_shared_plan(dks_ctx* ctx, int M, int* present) {
+    REQUIRE(ctx && present && M >= 0 && M <= DKS_MAX_GROUPS, "dks_has_shared_plan: bad arguments");
+    *present = (ctx->h_plans[M].z != nullptr && ctx->h_plans[M].S == dks_effective_S(M, ctx->nsamples_req)) ? 1 : 0;
+    return DKS_OK;
+}
+
+int dks_prepare_dev(dks_ctx* ctx, const double* X_dev, int n) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_prepare: call dks_fit first");
+    REQUIRE(X_dev && n > 0, "dks_prepare: need X and n > 0");
+    return launch_prepare(ctx, X_dev, n);
+}
+
+int dks_prepare_host(dks_ctx* ctx, const double* X_host, int n) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_prepare: call dks_fit first");
+    REQUIRE(X_host && n > 0, "dks_prepare: need X and n > 0");
+    size_t need = (size_t)n * ctx->D;
+    if (need > ctx->cap_X) { TRY(dev_alloc(&ctx->d_X, need)); ctx->cap_X = need; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_X, X_host, sizeof(double) * need, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_prepare(ctx, ctx->d_X, n);
+}
+
+int dks_get_m_histogram(dks_ctx* ctx, int32_t* hist_host) {
+    BIND(ctx);
+    REQUIRE(ctx->prepared && hist_host, "dks_get_m_histogram: call dks_prepare_* first");
+    int tmp[DKS_MAX_GROUPS + 1];
+    CUDA_TRY(cudaMemcpyAsync(tmp, ctx->d_hist, sizeof(tmp), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int m = 0; m <= ctx->G; ++m) hist_host[m] = tmp[m];
+    return DKS_OK;
+}
+
+int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host) {
+    BIND(ctx);
+    REQUIRE(ctx->prepared, "dks_get_varying: call dks_prepare_* first");
+    if (M_host) CUDA_TRY(cudaMemcpyAsync(M_host, ctx->d_M, sizeof(int) * ctx->cur_n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask_host)
+        CUDA_TRY(cudaMemcpyAsync(mask_host, ctx->d_vmask, sizeof(uint64_t) * ctx->cur_n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DKS_OK;
+}
+
+int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev, const double* ext_w_dev, int ext_stride) {
+    BIND(ctx);
+    REQUIRE(phi_dev, "dks_explain_dev: phi is NULL");
+    TRY(launch_explain(ctx, phi_dev, ext_zbits_dev, ext_w_dev, ext_stride));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    return DKS_OK;
+}
+
+int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
+                     const double* ext_w_host, int ext_stride) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_explain_host: call dks_fit first");
+    REQUIRE(X_host && phi_host && n > 0, "dks_explain_host: bad arguments");
+    TRY(dks_prepare_host(ctx, X_host, n));
+    size_t need_phi = (size_t)ctx->C * n * ctx->G;
+    if (need_phi > ctx->cap_phi) { TRY(dev_alloc(&ctx->d_phi, need_phi)); ctx->cap_phi = need_phi; }
+    const uint64_t* dz = nullptr; const double* dw = nullptr;
+    if (ext_zbits_host) {
+        REQUIRE(ext_w_host && ext_stride > 0, "dks_explain_host: ext_w / ext_stride missing");
+        size_t need = (size_t)n * ext_stride;
+        if (need > ctx->cap_ext) { TRY(dev_alloc(&ctx->d_extz, need)); TRY(dev_alloc(&ctx->d_extw, need)); ctx->cap_ext = need; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_extz, ext_zbits_host, sizeof(uint64_t) * need, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_extw, ext_w_host, sizeof(double) * need, cudaMemcpyHostToDevice, ctx->stream));
+        dz = ctx->d_extz; dw = ctx->d_extw;
+    }
+    TRY(launch_explain(ctx, ctx->d_phi, dz, dw, ext_stride));
+    CUDA_TRY(cudaMemcpyAsync(phi_host, ctx->d_phi, sizeof(double) * need_phi, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return check_status(ctx);
+}
+
+int dks_last_status(dks_ctx* ctx, int* detail) {
+    BIND(ctx);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (detail) *detail = ctx->h_status[1];
+    return check_status(ctx);
+}
+
+int dks_set_kernel(dks_ctx* ctx, int kernel) {
+    REQUIRE(ctx && kernel >= DKS_KERNEL_AUTO && kernel <= DKS_KERNEL_TCGEN05, "dks_set_kernel: unknown kernel %d", kernel);
+    ctx->kernel_choice = kernel;
+    return DKS_OK;
+}
+
+int dks_kernel_launches(dks_ctx* ctx, int64_t* count) {
+    REQUIRE(ctx && count, "dks_kernel_launches: bad arguments");
+    *count = ctx->launches;
+    return DKS_OK;
+}
+
+int dks_last_timings(dks_ctx* ctx, float* ms3) {
+    BIND(ctx);
+    REQUIRE(ms3 && ctx->prepared, "dks_last_timings: nothing to report");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventElapsedTime(&ms3[0], ctx->ev[0], ctx->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms3[1], ctx->ev[2], ctx->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms3[2], ctx->ev[0], ctx->ev[3]));
+    return DKS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Shared declarations of the B200 KernelSHAP engine (host context + device parameter blocks).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "dks.h"
+
+#define DKS_MAX_GROUPS 64  // one 64-bit word of coalition bits per row (multi-word plans: not yet)
+
+// ---- device-visible plan table entry: one shared coalition plan per number of varying groups M ----------
+struct PlanDev {
+    const uint64_t* z;   // [S] coalition bits in upstream row order
+    const double* w;     // [S] kernel weights
+    const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
+    const float* ainv;   // reserved
+    int S;
+    int pad;
+};
+
+// nsamples resolution of KernelExplainer.explain: 'auto' (req <= 0) = 2M + 2^11; capped at 2^M - 2 for M <= 30
+__host__ __device__ __forceinline__ int dks_effective_S(int M, int req) {
+    long long s = req > 0 ? (long long)req : 2LL * M + 2048;
+    if (M <= 30) {
+        long long mx = (1LL << M) - 2;
+        if (s > mx) s = mx;
+    }
+    return (int)s;
+}
+
+// ---- parameters of the fused coalition kernel ------------------------------------------------------------
+struct ExplainParams {
+    int n, N, G, R, C;
+    int act, link;
+    int S_req;
+    int S_cap;            // capacity of the per-CTA y buffer (max S any instance can need)
+    double scale;         // binary head: -kappa*log2(e); applied to grouped contributions
+    const float* BWs;     // [R][G][N] scaled grouped background contributions (k-major: column j contiguous)
+    const float* bases;   // [R][N]   scaled background scores
+    const float* wbf;     // [N]      background weights (float)
+    const double* wbg;    // [N]
+    const double* Bbar;   // [G][R]   weighted mean grouped background contribution (identity head)
+    const double* fnull;  // [C]
+    const double* linkfnull;  // [C]
+    const double* XW;     // [n][G][R] grouped instance contributions (unscaled)
+    const uint64_t* vmask;  // [n]
+    const int* Mcnt;      // [n]
+    const double* dlink;  // [n][C] link(f(x)) - link(fnull)
+    const PlanDev* plans; // [DKS_MAX_GROUPS + 1]
+    const uint64_t* ext_z;  // per-instance plans or NULL
+    const double* ext_w;
+    int ext_stride;
+    double* phi;          // [C][n][G]
+    int* status;          // [2] {code, detail}
+};
+
+struct dks_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+
+    // problem definition
+    int N = 0, D = 0, G = 0, R = 0, C = 0;
+    int act = -1, link = DKS_LINK_IDENTITY, scalar_out = 0;
+    double kappa = 1.0;
+    bool fitted = false;
+    int kernel_choice = DKS_KERNEL_AUTO;
+    int nsamples_req = 0;
+
+    // host copies
+    std::vector<double> h_bg, h_wbg, h_W, h_b;
+    std::vector<int32_t> h_goff, h_gcols;
+
+    // device, fit-time
+    double *d_bg = nullptr, *d_wbg = nullptr, *d_W = nullptr, *d_b = nullptr;
+    int32_t *d_goff = nullptr, *d_gcols = nullptr;
+    double *d_colmin = nullptr, *d_colmax = nullptr;
+    int* d_colnan = nullptr;
+    double *d_BW = nullptr, *d_scores = nullptr, *d_Bbar = nullptr, *d_fnull = nullptr, *d_linkfnull = nullptr;
+    float *d_BWs = nullptr, *d_bases = nullptr, *d_wbf = nullptr;
+    double scale = 1.0;
+    std::vector<double> h_fnull, h_linkfnull;
+
+    // plans
+    PlanDev h_plans[DKS_MAX_GROUPS + 1];
+    PlanDev* d_plans = nullptr;
+    std::vector<void*> plan_allocs;
+    int max_plan_S = 0;
+
+    // per-call workspace
+    int cap_n = 0, cur_n = 0;
+    bool prepared = false;
+    double* d_X = nullptr;       // staging for host inputs
+    size_t cap_X = 0;
+    const double* cur_X = nullptr;
+    double* d_XW = nullptr;
+    unsigned char* d_vflag = nullptr;
+    uint64_t* d_vmask = nullptr;
+    int* d_M = nullptr;
+    double* d_dlink = nullptr;
+    int* d_hist = nullptr;
+    int* d_status = nullptr;
+    double* d_phi = nullptr;
+    size_t cap_phi = 0;
+    uint64_t* d_extz = nullptr;
+    double* d_extw = nullptr;
+    size_t cap_ext = 0;
+    int h_status[2] = {0, 0};
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t launches = 0;
+};

@@ -1,0 +1,503 @@
+// Device code of the B200 KernelSHAP engine: fit kernels (K0), per-instance preparation, and the fused
+// coalition kernel (mask/impute + predict + background reduction + link + constrained WLS).
+//
+// Algebra used throughout: the model head sees linear scores, so a masked row's score is
+//     score(s, j) = base_j + sum_{k in varying} z_sk * (XW_i[k] - BW[j][k])
+// with XW_i[k] = sum_{col in group k} x_i[col] W[col]  and  BW[j][k] likewise for background row j.  The
+// masked batch (S*N x D, KernelExplainer.allocate/addsample) is therefore never materialised.
+#pragma once
+
+#include "dks_common.cuh"
+
+namespace dks {
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// np.isclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=True) as used by KernelExplainer.not_equal
+__device__ __forceinline__ bool np_isclose(double a, double b) {
+    if (a == b) return true;
+    if (isnan(a) && isnan(b)) return true;
+    if (!isfinite(a) || !isfinite(b)) return false;
+    return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b);
+}
+
+// link(p): shap.common.LogitLink.f / IdentityLink.f
+__device__ __forceinline__ double link_f(double p, int link) {
+    return link == DKS_LINK_LOGIT ? log(p / (1.0 - p)) : p;
+}
+
+// model head in float64 on R scores -> C outputs (C = 2 for the binary head, else R)
+__device__ inline void head_f64(const double* z, int R, int act, double kappa, double* out) {
+    if (act == DKS_ACT_BINARY_LOGISTIC) {
+        // softmax([-kz/2, kz/2]) evaluated the numerically stable way sklearn does
+        double t = kappa * z[0];
+        double e = exp(-fabs(t));
+        double big = 1.0 / (1.0 + e), small = e / (1.0 + e);
+        out[1] = t >= 0 ? big : small;
+        out[0] = t >= 0 ? small : big;
+    } else if (act == DKS_ACT_SOFTMAX) {
+        double m = z[0];
+        for (int r = 1; r < R; ++r) m = fmax(m, z[r]);
+        double sum = 0;
+        for (int r = 0; r < R; ++r) { out[r] = exp(z[r] - m); sum += out[r]; }
+        for (int r = 0; r < R; ++r) out[r] /= sum;
+    } else {
+        for (int r = 0; r < R; ++r) out[r] = z[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K0: fit (DenseData + KernelExplainer.__init__)
+// ------------------------------------------------------------------------------------------------------
+// BW[j][g][r] = sum_{col in g} bg[j][col] * W[r][col]
+__global__ void fit_bw_kernel(const double* __restrict__ bg, const double* __restrict__ W,
+                              const int32_t* __restrict__ goff, const int32_t* __restrict__ gcols, int N, int D,
+                              int G, int R, double* __restrict__ BW) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * G * R) return;
+    int r = idx % R, g = (idx / R) % G, j = idx / (R * G);
+    double acc = 0;
+    for (int c = goff[g]; c < goff[g + 1]; ++c) {
+        int col = gcols[c];
+        acc += bg[(size_t)j * D + col] * W[(size_t)r * D + col];
+    }
+    BW[idx] = acc;
+}
+
+__global__ void fit_scores_kernel(const double* __restrict__ BW, const double* __restrict__ b, int N, int G, int R,
+                                  double* __restrict__ scores) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * R) return;
+    int r = idx % R, j = idx / R;
+    double acc = b[r];
+    for (int g = 0; g < G; ++g) acc += BW[((size_t)j * G + g) * R + r];
+    scores[idx] = acc;
+}
+
+__global__ void fit_colstats_kernel(const double* __restrict__ bg, int N, int D, double* __restrict__ colmin,
+                                    double* __restrict__ colmax, int* __restrict__ colnan) {
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= D) return;
+    double mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    for (int j = 0; j < N; ++j) {
+        double v = bg[(size_t)j * D + col];
+        if (isnan(v)) nan = 1;
+        else { mn = fmin(mn, v); mx = fmax(mx, v); }
+    }
+    colmin[col] = mn; colmax[col] = mx; colnan[col] = nan;
+}
+
+// fnull[c] = sum_j w_j f(bg_j)[c]; linkfnull = link(fnull); Bbar[g][r] = sum_j w_j BW[j][g][r].  One block.
+__global__ void fit_fnull_kernel(const double* __restrict__ scores, const double* __restrict__ BW,
+                                 const double* __restrict__ wbg, int N, int G, int R, int C, int act, double kappa,
+                                 int link, double* __restrict__ fnull, double* __restrict__ linkfnull,
+                                 double* __restrict__ Bbar) {
+    int t = threadIdx.x;
+    if (t < C) {
+        double acc = 0;
+        for (int j = 0; j < N; ++j) {
+            double out[DKS_MAX_GROUPS];
+            head_f64(scores + (size_t)j * R, R, act, kappa, out);
+            acc += out[t] * wbg[j];
+        }
+        fnull[t] = acc;
+        linkfnull[t] = link_f(acc, link);
+    }
+    for (int idx = t; idx < G * R; idx += blockDim.x) {
+        double acc = 0;
+        for (int j = 0; j < N; ++j) acc += wbg[j] * BW[(size_t)j * G * R + idx];
+        Bbar[idx] = acc;
+    }
+}
+
+// scaled float copies consumed by the fused kernel: BWs[r][g][j] = scale*BW[j][g][r], bases[r][j] = scale*score
+__global__ void fit_scale_kernel(const double* __restrict__ BW, const double* __restrict__ scores,
+                                 const double* __restrict__ wbg, int N, int G, int R, double scale,
+                                 float* __restrict__ BWs, float* __restrict__ bases, float* __restrict__ wbf) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N * G * R) {
+        int j = idx % N, g = (idx / N) % G, r = idx / (N * G);
+        BWs[idx] = (float)(scale * BW[((size_t)j * G + g) * R + r]);
+    }
+    if (idx < N * R) {
+        int j = idx % N, r = idx / N;
+        bases[idx] = (float)(scale * scores[(size_t)j * R + r]);
+    }
+    if (idx < N) wbf[idx] = (float)wbg[idx];
+}
+
+// f(X) for n rows, float64 (model check against the Python callable)
+__global__ void predict_kernel(const double* __restrict__ X, const double* __restrict__ W,
+                               const double* __restrict__ b, int n, int D, int R, int C, int act, double kappa,
+                               double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z[DKS_MAX_GROUPS], o[DKS_MAX_GROUPS];
+    for (int r = 0; r < R; ++r) {
+        double acc = b[r];
+        for (int c = 0; c < D; ++c) acc += X[(size_t)i * D + c] * W[(size_t)r * D + c];
+        z[r] = acc;
+    }
+    head_f64(z, R, act, kappa, o);
+    for (int c = 0; c < C; ++c) out[(size_t)i * C + c] = o[c];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Preparation: grouped instance contributions, varying_groups(), f(x), link deltas
+// ------------------------------------------------------------------------------------------------------
+// one thread per (instance, group): XW[i][g][r] and the "group varies" flag (KernelExplainer.varying_groups)
+__global__ void prep_group_kernel(const double* __restrict__ X, const double* __restrict__ W,
+                                  const double* __restrict__ bg, const int32_t* __restrict__ goff,
+                                  const int32_t* __restrict__ gcols, const double* __restrict__ colmin,
+                                  const double* __restrict__ colmax, const int* __restrict__ colnan, int n, int N,
+                                  int D, int G, int R, double* __restrict__ XW, unsigned char* __restrict__ vflag) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * G) return;
+    int g = idx % G, i = idx / G;
+    bool varies = false;
+    double acc[8];
+    for (int r = 0; r < R && r < 8; ++r) acc[r] = 0;
+    for (int c = goff[g]; c < goff[g + 1]; ++c) {
+        int col = gcols[c];
+        double xv = X[(size_t)i * D + col];
+        for (int r = 0; r < R && r < 8; ++r) acc[r] += xv * W[(size_t)r * D + col];
+        if (!varies) {
+            if (colnan[col] || isnan(xv)) {
+                for (int j = 0; j < N && !varies; ++j) varies = !np_isclose(xv, bg[(size_t)j * D + col]);
+            } else {
+                // |x-b| - rtol|b| is decreasing for b <= x and increasing for b >= x: the extremes decide
+                varies = !np_isclose(xv, colmin[col]) || !np_isclose(xv, colmax[col]);
+            }
+        }
+    }
+    for (int r = 0; r < R && r < 8; ++r) XW[(size_t)idx * R + r] = acc[r];
+    vflag[idx] = varies ? 1 : 0;
+}
+
+// one thread per instance: varying bit-mask, M, histogram of M, f(x), link(f(x)) - link(fnull)
+__global__ void prep_instance_kernel(const double* __restrict__ XW, const unsigned char* __restrict__ vflag,
+                                     const double* __restrict__ b, const double* __restrict__ linkfnull, int n,
+                                     int G, int R, int C, int act, double kappa, int link,
+                                     uint64_t* __restrict__ vmask, int* __restrict__ Mcnt,
+                                     double* __restrict__ dlink, int* __restrict__ hist) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t m = 0;
+    double z[8], o[DKS_MAX_GROUPS];
+    for (int r = 0; r < R; ++r) z[r] = b[r];
+    for (int g = 0; g < G; ++g) {
+        if (vflag[(size_t)i * G + g]) m |= (1ull << g);
+        for (int r = 0; r < R; ++r) z[r] += XW[((size_t)i * G + g) * R + r];
+    }
+    int M = __popcll(m);
+    vmask[i] = m;
+    Mcnt[i] = M;
+    atomicAdd(&hist[M], 1);
+    head_f64(z, R, act, kappa, o);
+    for (int c = 0; c < C; ++c) dlink[(size_t)i * C + c] = link_f(o[c], link) - linkfnull[c];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Constrained WLS (KernelExplainer.solve without the l1 branch), float64, one CTA
+// ------------------------------------------------------------------------------------------------------
+// With L the last varying position and z' = (z_L ? ~z : z):  e_k e_l = z'_k & z'_l  and  e_k = (z_L ? -1 : 1) z'_k,
+// where e_k = z_k - z_L is a column of upstream's `etmp`.
+
+// A = E^T diag(w) E for k,l < M-1 (symmetric, row-major nA x nA), built warp-per-entry
+__device__ inline void wls_build_normal(const uint64_t* __restrict__ zp, const double* __restrict__ wp, int S, int M,
+                                        double* A) {
+    const int nA = M - 1, L = M - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int npairs = nA * (nA + 1) / 2;
+    for (int pr = warp; pr < npairs; pr += nwarps) {
+        int k = 0, rem = pr;
+        while (rem > k) { rem -= (k + 1); ++k; }  // pr = k(k+1)/2 + l, l <= k
+        int l = rem;
+        double acc = 0;
+        for (int s = lane; s < S; s += 32) {
+            uint64_t z = zp[s];
+            if ((z >> L) & 1ull) z = ~z;
+            if (((z >> k) & (z >> l)) & 1ull) acc += wp[s];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) { A[k * nA + l] = acc; A[l * nA + k] = acc; }
+    }
+}
+
+// in-place lower Cholesky of the nA x nA matrix A (row-major) by warp 0; returns false if not positive definite
+__device__ inline bool wls_cholesky_warp(double* A, int nA) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    for (int c = 0; c < nA; ++c) {
+        double d = A[c * nA + c];
+        if (!(d > 0.0)) ok = false;
+        d = sqrt(d);
+        __syncwarp();
+        if (lane == 0) A[c * nA + c] = d;
+        for (int r = c + 1 + lane; r < nA; r += 32) A[r * nA + c] /= d;
+        __syncwarp();
+        for (int r = c + 1 + lane; r < nA; r += 32) {
+            double lrc = A[r * nA + c];
+            for (int c2 = c + 1; c2 <= r; ++c2) A[r * nA + c2] -= lrc * A[c2 * nA + c];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// rhs[k] = sum_s w_s e_sk (y_s - z_sL * delta), warp-per-k
+__device__ inline void wls_build_rhs(const uint64_t* __restrict__ zp, const double* __restrict__ wp,
+                                     const double* ys, int S, int M, double delta, double* rhs) {
+    const int nA = M - 1, L = M - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < nA; k += nwarps) {
+        double acc = 0;
+        for (int s = lane; s < S; s += 32) {
+            uint64_t z = zp[s];
+            int zl = (int)((z >> L) & 1ull), zk = (int)((z >> k) & 1ull);
+            int e = zk - zl;
+            if (e != 0) {
+                double yy = ys[s] - (zl ? delta : 0.0);
+                acc += wp[s] * (double)e * yy;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) rhs[k] = acc;
+    }
+}
+
+// solve (L L^T) beta = rhs in place (thread 0), then write phi for output dim c of instance i
+__device__ inline void wls_solve_write(const double* Lf, double* rhs, int M, double delta, const int* vi,
+                                       double* __restrict__ phi_row, double sign) {
+    const int nA = M - 1;
+    for (int r = 0; r < nA; ++r) {
+        double v = rhs[r];
+        for (int c = 0; c < r; ++c) v -= Lf[r * nA + c] * rhs[c];
+        rhs[r] = v / Lf[r * nA + r];
+    }
+    for (int r = nA - 1; r >= 0; --r) {
+        double v = rhs[r];
+        for (int c = r + 1; c < nA; ++c) v -= Lf[c * nA + r] * rhs[c];
+        rhs[r] = v / Lf[r * nA + r];
+    }
+    double sum = 0;
+    for (int k = 0; k < nA; ++k) {
+        double v = rhs[k];
+        sum += v;
+        if (fabs(v) < 1e-10) v = 0;
+        phi_row[vi[k]] = sign * v;
+    }
+    double last = delta - sum;
+    if (fabs(last) < 1e-10) last = 0;
+    phi_row[vi[nA]] = sign * last;
+}
+
+// factor the normal matrix of a shared plan once (dks_set_shared_plan): one CTA
+__global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int S, int M,
+                                   double* __restrict__ chol, int* __restrict__ status) {
+    extern __shared__ double sm_d[];
+    double* A = sm_d;
+    const int nA = M - 1;
+    wls_build_normal(z, w, S, M, A);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bool ok = wls_cholesky_warp(A, nA);
+        if (!ok && threadIdx.x == 0) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) chol[idx] = A[idx];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fused coalition kernel, CUDA-core (SIMT) version.  One CTA per instance (grid-stride), one thread per
+// coalition row.  Handles the binary-logistic and identity heads; any plan source.
+// ------------------------------------------------------------------------------------------------------
+struct SimtSmem {
+    double* ys;     // [S_cap] link(ey) - link(fnull) per coalition
+    double* A;      // [63*63] normal matrix / its Cholesky factor
+    double* rhs;    // [64]
+    double* xw;     // [64] scaled grouped contributions of the instance (varying positions)
+    int* vi;        // [64] varying position -> group index
+    float* Bs;      // [M][N] scaled grouped background contributions of the varying groups, then bases[N], wb[N]
+};
+
+__device__ inline SimtSmem simt_carve(unsigned char* base, int S_cap) {
+    SimtSmem s;
+    s.ys = reinterpret_cast<double*>(base);
+    s.A = s.ys + S_cap;
+    s.rhs = s.A + 63 * 63;
+    s.xw = s.rhs + 64;
+    s.vi = reinterpret_cast<int*>(s.xw + 64);
+    s.Bs = reinterpret_cast<float*>(s.vi + 64);
+    return s;
+}
+
+__host__ __device__ inline size_t simt_smem_bytes(int S_cap, int N, int Mmax) {
+    return sizeof(double) * ((size_t)S_cap + 63 * 63 + 64 + 64) + sizeof(int) * 64 +
+           sizeof(float) * ((size_t)Mmax * N + 2 * (size_t)N);
+}
+
+__global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimtSmem sm = simt_carve(smem_raw, p.S_cap);
+    const int tid = threadIdx.x;
+    const int N = p.N, G = p.G, C = p.C;
+    const size_t slab = (size_t)p.n * G;
+
+    for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
+        const int M = p.Mcnt[i];
+        const uint64_t vm = p.vmask[i];
+        __syncthreads();  // previous instance done with shared memory
+        for (int idx = tid; idx < C * G; idx += blockDim.x) p.phi[(size_t)(idx / G) * slab + (size_t)i * G + idx % G] = 0.0;
+        if (M == 0) continue;
+        if (M == 1) {
+            if (tid < C) {
+                int g = __ffsll((long long)vm) - 1;
+                p.phi[(size_t)tid * slab + (size_t)i * G + g] = p.dlink[(size_t)i * C + tid];
+            }
+            continue;
+        }
+        const int S = dks_effective_S(M, p.S_req);
+        const uint64_t* zp;
+        const double* wp;
+        const double* chol = nullptr;
+        if (p.ext_z != nullptr) {
+            zp = p.ext_z + (size_t)i * p.ext_stride;
+            wp = p.ext_w + (size_t)i * p.ext_stride;
+        } else {
+            PlanDev pd = p.plans[M];
+            if (pd.z == nullptr || pd.S != S) {
+                if (tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING); p.status[1] = M; }
+                continue;
+            }
+            zp = pd.z; wp = pd.w; chol = pd.chol;
+        }
+        if (S > p.S_cap) {
+            if (tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_INVALID); p.status[1] = i; }
+            continue;
+        }
+
+        if (tid == 0) {
+            int k = 0;
+            for (int g = 0; g < G; ++g) if ((vm >> g) & 1ull) sm.vi[k++] = g;
+        }
+        __syncthreads();
+
+        float* Bs = sm.Bs;
+        float* bases = Bs + (size_t)M * N;
+        float* wb = bases + N;
+
+        if (p.act == DKS_ACT_BINARY_LOGISTIC) {
+            // stage this instance's varying columns of the background table
+            for (int idx = tid; idx < M * N; idx += blockDim.x) {
+                int k = idx / N, j = idx - k * N;
+                Bs[idx] = p.BWs[(size_t)sm.vi[k] * N + j];
+            }
+            for (int j = tid; j < N; j += blockDim.x) { bases[j] = p.bases[j]; wb[j] = p.wbf[j]; }
+            if (tid < M) sm.xw[tid] = p.scale * p.XW[(size_t)i * G + sm.vi[tid]];
+            __syncthreads();
+
+            const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
+            for (int s = tid; s < S; s += blockDim.x) {
+                const uint64_t z = zp[s];
+                double a = 0;
+                for (int k = 0; k < M; ++k) if ((z >> k) & 1ull) a += sm.xw[k];
+                const float af = (float)a;
+                float acc1 = 0.f, acc0 = 0.f;
+                for (int j = 0; j < N; ++j) {
+                    float c = 0.f;
+                    for (int k = 0; k < M; ++k) if ((z >> k) & 1ull) c += Bs[k * N + j];
+                    float t = (bases[j] - c) + af;     // = -kappa*log2(e) * masked score
+                    t = fminf(fmaxf(t, -120.f), 120.f);
+                    float u = ex2_approx(t);           // exp(-kappa*score)
+                    float r = rcp_approx(1.f + u);     // p1 = sigmoid(kappa*score)
+                    acc1 = fmaf(wb[j], r, acc1);
+                    acc0 = fmaf(wb[j], u * r, acc0);   // p0 = 1 - p1, accumulated without cancellation
+                }
+                double y;
+                if (p.link == DKS_LINK_LOGIT) y = log((double)acc1 / (double)acc0) - lf1;
+                else y = (double)acc1 - f1;
+                sm.ys[s] = y;
+            }
+            __syncthreads();
+
+            // WLS for output 1; output 0 is its exact negation (p0 = 1 - p1 row-wise)
+            const double* Lf;
+            if (chol != nullptr) {
+                for (int idx = tid; idx < (M - 1) * (M - 1); idx += blockDim.x) sm.A[idx] = chol[idx];
+            } else {
+                wls_build_normal(zp, wp, S, M, sm.A);
+                __syncthreads();
+                if (tid < 32) {
+                    bool ok = wls_cholesky_warp(sm.A, M - 1);
+                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                }
+            }
+            Lf = sm.A;
+            const double delta = p.dlink[(size_t)i * C + 1];
+            wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs);
+            __syncthreads();
+            if (tid == 0) {
+                wls_solve_write(Lf, sm.rhs, M, delta, sm.vi, p.phi + slab + (size_t)i * G, 1.0);
+                double* phi0 = p.phi + (size_t)i * G;
+                const double* phi1 = p.phi + slab + (size_t)i * G;
+                for (int k = 0; k < M; ++k) { double v = phi1[sm.vi[k]]; phi0[sm.vi[k]] = (v == 0.0) ? 0.0 : -v; }
+            }
+        } else if (p.act == DKS_ACT_IDENTITY) {
+            // identity head: the background average commutes with the head, so
+            // ey_r(s) = fnull_r + sum_k z_sk (XW_i[k][r] - Bbar[k][r])   -- float64 throughout
+            const double* Lf;
+            if (chol != nullptr) {
+                for (int idx = tid; idx < (M - 1) * (M - 1); idx += blockDim.x) sm.A[idx] = chol[idx];
+            } else {
+                wls_build_normal(zp, wp, S, M, sm.A);
+                __syncthreads();
+                if (tid < 32) {
+                    bool ok = wls_cholesky_warp(sm.A, M - 1);
+                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                }
+            }
+            Lf = sm.A;
+            for (int r = 0; r < p.R; ++r) {
+                __syncthreads();
+                if (tid < M) {
+                    int g = sm.vi[tid];
+                    sm.xw[tid] = p.XW[((size_t)i * G + g) * p.R + r] - p.Bbar[(size_t)g * p.R + r];
+                }
+                __syncthreads();
+                const double fn = p.fnull[r], lfn = p.linkfnull[r];
+                for (int s = tid; s < S; s += blockDim.x) {
+                    const uint64_t z = zp[s];
+                    double a = fn;
+                    for (int k = 0; k < M; ++k) if ((z >> k) & 1ull) a += sm.xw[k];
+                    sm.ys[s] = link_f(a, p.link) - lfn;
+                }
+                __syncthreads();
+                const double delta = p.dlink[(size_t)i * C + r];
+                wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs);
+                __syncthreads();
+                if (tid == 0) wls_solve_write(Lf, sm.rhs, M, delta, sm.vi, p.phi + (size_t)r * slab + (size_t)i * G, 1.0);
+            }
+        }
+    }
+}
+
+}  // namespace dks

@@ -1,0 +1,304 @@
+"""``GpuKernelExplainer``: the object that sits in ``KernelShap._explainer``.
+
+In the reference that slot holds ``KernelExplainerWrapper`` (explainers/kernel_shap.py:217-261), a subclass of
+``shap.KernelExplainer``; ``KernelShap`` only needs ``get_explanation(X, **kwargs)``, ``.expected_value`` and
+``.vector_out`` from it (kernel_shap.py:789-790, :880-887).  This class keeps that constructor shape
+``(predictor, background_data, link=..., seed=...)`` and those members, and runs the per-instance hot path
+(varying groups -> coalition plan -> mask/impute -> predict -> background mean -> link -> constrained WLS) in
+CUDA through the C ABI of ``include/dks.h``.  No CPU fallback: without ``libdks.so`` and a B200 it raises.
+"""
+import ctypes as C
+import logging
+
+import numpy as np
+
+from . import _cabi
+from .data import DenseData, convert_to_data, convert_to_link
+from .plan import build_plan, pack_dense_plan, resolve_nsamples
+from .predictors import extract_linear_spec
+
+logger = logging.getLogger(__name__)
+
+MODEL_CHECK_RTOL = 1e-9
+
+
+class GpuKernelExplainer:
+    """CUDA KernelSHAP explainer with the interface of ``shap.KernelExplainer`` / ``KernelExplainerWrapper``.
+
+    Parameters
+    ----------
+    model
+        What the reference passes as ``predictor``: a bound ``predict_proba`` / ``decision_function`` of a linear
+        model, or a ``LinearModelSpec`` (see ``predictors.extract_linear_spec``).
+    data
+        Background data: array, DataFrame or ``DenseData`` (groups and weights honoured).
+    link
+        ``'identity'`` or ``'logit'``.
+    seed
+        As in ``KernelExplainerWrapper.__init__`` (kernel_shap.py:225-228): seeds the global legacy NumPy stream the
+        sampled part of the coalition plans is drawn from.
+    device
+        CUDA device ordinal (default: ``LOCAL_RANK`` under torchrun, else 0).
+    """
+
+    def __init__(self, model, data, link="identity", seed=None, device=None, kernel="auto", **kwargs):
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        if seed is not None:
+            np.random.seed(seed)
+        self.lib = _cabi.load()
+        self.link = convert_to_link(link)
+        self.model_callable = model
+        self.spec = extract_linear_spec(model)
+        self.data = convert_to_data(data)
+        if self.data.transposed:
+            raise NotImplementedError("transposed DenseData (group sizes matching axis 0) is not supported")
+        bg = np.ascontiguousarray(np.asarray(self.data.data, dtype=np.float64))
+        if bg.ndim != 2:
+            raise TypeError("background data must be two-dimensional")
+        self.N, self.P = bg.shape
+        if self.spec.W.shape[1] != self.P:
+            raise ValueError(f"model expects {self.spec.W.shape[1]} columns, background has {self.P}")
+        if self.N > 100:
+            logger.warning("Using %d background data samples could cause slower run times. Consider using "
+                           "shap.sample(data, K) or shap.kmeans(data, K) to summarize the background as K samples.",
+                           self.N)
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = int(device)
+
+        self._ctx = C.c_void_p()
+        _cabi.check(self.lib.dks_create(C.byref(self._ctx), self.device))
+        weights = np.ascontiguousarray(self.data.weights, dtype=np.float64)
+        _cabi.check(self.lib.dks_set_background(self._ctx, _cabi.ptr(bg), self.N, self.P, _cabi.ptr(weights)))
+        offsets = np.zeros(self.data.groups_size + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(g) for g in self.data.groups])
+        cols = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.int32) for g in self.data.groups]), dtype=np.int32)
+        _cabi.check(self.lib.dks_set_groups(self._ctx, _cabi.ptr(offsets), _cabi.ptr(cols), self.data.groups_size))
+        _cabi.check(self.lib.dks_set_model(self._ctx, _cabi.ptr(self.spec.W), _cabi.ptr(self.spec.b), self.spec.W.shape[0],
+                                           self.spec.act_code, self.spec.kappa, int(self.spec.scalar_out)))
+        link_code = _cabi.LINK_LOGIT if str(self.link) == "logit" else _cabi.LINK_IDENTITY
+        _cabi.check(self.lib.dks_set_link(self._ctx, link_code))
+        self.set_kernel(kernel)
+        _cabi.check(self.lib.dks_fit(self._ctx))
+
+        self.D = self.spec.n_outputs
+        fnull = np.zeros(self.D)
+        expected = np.zeros(self.D)
+        _cabi.check(self.lib.dks_get_fnull(self._ctx, _cabi.ptr(fnull), _cabi.ptr(expected)))
+        self.vector_out = not self.spec.scalar_out
+        self.fnull = fnull
+        self.expected_value = expected if self.vector_out else float(expected[0])
+        self._nsamples_req = None
+        self._check_model_against_callable(bg)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _check_model_against_callable(self, bg):
+        """The extracted linear model must reproduce the user's callable on the background rows."""
+        if not callable(self.model_callable):
+            return
+        want = np.asarray(self.model_callable(bg), dtype=np.float64).reshape(self.N, -1)
+        got = self.predict(bg)
+        if want.shape != got.shape or not np.allclose(got, want, rtol=1e-7, atol=1e-9):
+            raise ValueError("the linear model extracted from `predictor` does not reproduce predictor(background): "
+                             "refusing to explain a different function (max abs diff "
+                             f"{np.max(np.abs(got - want)) if want.shape == got.shape else 'shape mismatch'})")
+
+    def predict(self, X):
+        """Model outputs [n, C] computed on the GPU in float64."""
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        out = np.zeros((X.shape[0], self.D))
+        _cabi.check(self.lib.dks_predict_host(self._ctx, _cabi.ptr(X), X.shape[0], _cabi.ptr(out)))
+        return out
+
+    def set_kernel(self, kernel):
+        code = {"auto": _cabi.KERNEL_AUTO, "simt": _cabi.KERNEL_SIMT, "tcgen05": _cabi.KERNEL_TCGEN05}[kernel]
+        _cabi.check(self.lib.dks_set_kernel(self._ctx, code))
+        self.kernel = kernel
+
+    # ------------------------------------------------------------------------------------------------------
+    def _set_nsamples(self, nsamples):
+        req = 0 if nsamples in ("auto", None) else int(nsamples)
+        if req != self._nsamples_req:
+            _cabi.check(self.lib.dks_set_nsamples(self._ctx, req))
+            self._nsamples_req = req
+
+    def _l1_guard(self, l1_reg, nsamples, hist=None):
+        """The engine solves the plain constrained WLS.  Upstream's ``solve`` first runs an l1 feature selection when
+        ``l1_reg`` asks for it, or under 'auto' when fewer than 20% of the coalition space is evaluated.  Never differ
+        silently: refuse those cases."""
+        if l1_reg in (False, 0):
+            return False
+        if l1_reg != "auto":
+            raise NotImplementedError(f"l1_reg={l1_reg!r}: l1 feature selection is not implemented in the CUDA engine; "
+                                      "pass l1_reg=False")
+        risky = []
+        for M in range(2, self.data.groups_size + 1):
+            if hist is not None and hist[M] == 0:
+                continue
+            S, max_s = resolve_nsamples(M, nsamples)
+            if S / max_s < 0.2:
+                risky.append(M)
+        if risky and hist is not None:
+            raise NotImplementedError(
+                f"l1_reg='auto' would run LassoLarsIC feature selection for instances with M in {risky} varying groups "
+                "(under 20% of the coalition space sampled); the CUDA engine implements the plain WLS only -- pass "
+                "l1_reg=False (as SURVEY.md §7 prescribes for both sides of a comparison)")
+        return bool(risky)
+
+    def _ensure_shared_plans(self, hist, nsamples):
+        for M in range(2, self.data.groups_size + 1):
+            if hist[M] == 0:
+                continue
+            present = C.c_int(0)
+            _cabi.check(self.lib.dks_has_shared_plan(self._ctx, M, C.byref(present)))
+            if present.value:
+                continue
+            plan = build_plan(M, nsamples)  # draws from the global legacy stream, like the reference
+            _cabi.check(self.lib.dks_set_shared_plan(self._ctx, M, plan.S, _cabi.ptr(plan.zbits), _cabi.ptr(plan.weights)))
+
+    def m_histogram(self):
+        hist = np.zeros(self.data.groups_size + 1, dtype=np.int32)
+        _cabi.check(self.lib.dks_get_m_histogram(self._ctx, _cabi.ptr(hist)))
+        return hist
+
+    def varying(self, X):
+        """(M [n], bit-mask [n]) of ``KernelExplainer.varying_groups`` for every row of X (GPU)."""
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), X.shape[0]))
+        M = np.zeros(X.shape[0], dtype=np.int32)
+        mask = np.zeros(X.shape[0], dtype=np.uint64)
+        _cabi.check(self.lib.dks_get_varying(self._ctx, _cabi.ptr(M), _cabi.ptr(mask)))
+        return M, mask
+
+    # ------------------------------------------------------------------------------------------------------
+    def shap_values(self, X, **kwargs):
+        """``KernelExplainer.shap_values``: list of C arrays [n, groups] (vector output) or one array.
+
+        kwargs: ``nsamples`` ('auto' | int), ``l1_reg`` ('auto' | False | 0), ``silent`` (ignored), and
+        ``plans`` = per-instance coalition plans ``[(Z [S_i, M_i] | zbits [S_i], w [S_i]) | None, ...]`` evaluated
+        instead of the engine's own shared plans (this is how tests give the oracle and the GPU identical inputs)."""
+        nsamples = kwargs.pop("nsamples", "auto")
+        l1_reg = kwargs.pop("l1_reg", "auto")
+        plans = kwargs.pop("plans", None)
+        kwargs.pop("silent", None)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        try:
+            import pandas as pd
+            if isinstance(X, (pd.DataFrame, pd.Series)):
+                X = X.values
+        except ImportError:  # pragma: no cover
+            pass
+        try:
+            from scipy import sparse
+            if sparse.issparse(X):
+                X = X.toarray()
+        except ImportError:  # pragma: no cover
+            pass
+        X = np.asarray(X, dtype=np.float64)
+        single = X.ndim == 1
+        if single:
+            X = X.reshape(1, -1)
+        assert X.ndim == 2, "Instance must have 1 or 2 dimensions!"
+        if X.shape[1] != self.P:
+            raise ValueError(f"X has {X.shape[1]} columns, background has {self.P}")
+        X = np.ascontiguousarray(X)
+        n, G = X.shape[0], self.data.groups_size
+        self._set_nsamples(nsamples)
+        need_hist = self._l1_guard(l1_reg, nsamples)
+
+        phi = np.zeros((self.D, n, G))
+        if plans is not None:
+            zb, w, stride = self._pack_external_plans(plans, n, nsamples)
+            if need_hist:
+                _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), n))
+                self._l1_guard(l1_reg, nsamples, self.m_histogram())
+            _cabi.check(self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), _cabi.ptr(zb), _cabi.ptr(w),
+                                                  stride))
+        else:
+            if need_hist:
+                _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), n))
+                hist = self.m_histogram()
+                self._l1_guard(l1_reg, nsamples, hist)
+                self._ensure_shared_plans(hist, nsamples)
+            rc = self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), None, None, 0)
+            if rc == _cabi.DKS_ERR_PLAN_MISSING:
+                # first call (or a new M): build the missing plans from the M histogram and run again
+                self._ensure_shared_plans(self.m_histogram(), nsamples)
+                rc = self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), None, None, 0)
+            _cabi.check(rc)
+
+        if not self.vector_out:
+            return phi[0, 0] if single else phi[0]
+        if single:
+            return [phi[c, 0] for c in range(self.D)]
+        return [phi[c] for c in range(self.D)]
+
+    def _pack_external_plans(self, plans, n, nsamples):
+        if len(plans) != n:
+            raise ValueError(f"got {len(plans)} plans for {n} instances")
+        stride = max([len(p[1]) for p in plans if p is not None and p[1] is not None] + [2])
+        zb = np.zeros((n, stride), dtype=np.uint64)
+        w = np.zeros((n, stride), dtype=np.float64)
+        for i, p in enumerate(plans):
+            if p is None or p[1] is None:
+                continue
+            Z, wi = p[-2], np.asarray(p[-1], dtype=np.float64)
+            Z = np.asarray(Z)
+            bits = pack_dense_plan(Z) if Z.ndim == 2 else Z.astype(np.uint64)
+            zb[i, :len(bits)] = bits
+            w[i, :len(wi)] = wi
+        return zb, w, stride
+
+    # ---- device-resident API (torch tensors appear only as raw pointers) ---------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        """Enqueue the engine's work on the given ``cudaStream_t`` (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        _cabi.check(self.lib.dks_set_stream(self._ctx, C.c_void_p(int(cuda_stream_ptr))))
+
+    def explain_device(self, X_dev_ptr, n, phi_dev_ptr, nsamples="auto"):
+        """Asynchronously explain ``n`` rows resident in device memory (float64 [n, D] at ``X_dev_ptr``) into the device
+        buffer ``phi_dev_ptr`` (float64 [C, n, G]) using the shared plans already on the device.  Call ``check_status()``
+        after synchronising to learn about missing plans / numerical failures."""
+        self._set_nsamples(nsamples)
+        _cabi.check(self.lib.dks_prepare_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n)))
+        _cabi.check(self.lib.dks_explain_dev(self._ctx, C.c_void_p(int(phi_dev_ptr)), None, None, 0))
+
+    def check_status(self):
+        """Synchronise the engine's stream and raise if the last explain reported a problem."""
+        detail = C.c_int(0)
+        _cabi.check(self.lib.dks_last_status(self._ctx, C.byref(detail)))
+
+    # ---- KernelExplainerWrapper members (kernel_shap.py:231-261) ---------------------------------------------
+    def get_explanation(self, X, **kwargs):
+        """Accepts an array, or a ``(batch_index, batch)`` tuple when called from a distributed context."""
+        if isinstance(X, tuple):
+            batch_idx, batch = X
+            return batch_idx, self.shap_values(batch, **kwargs)
+        return self.shap_values(X, **kwargs)
+
+    def return_attribute(self, name):
+        return self.__getattribute__(name)
+
+    # ---- introspection used by bench.py / tests -----------------------------------------------------------------
+    def kernel_launches(self):
+        v = C.c_int64(0)
+        _cabi.check(self.lib.dks_kernel_launches(self._ctx, C.byref(v)))
+        return int(v.value)
+
+    def last_timings_ms(self):
+        out = np.zeros(3, dtype=np.float32)
+        _cabi.check(self.lib.dks_last_timings(self._ctx, _cabi.ptr(out)))
+        return {"prepare": float(out[0]), "coalitions": float(out[1]), "total": float(out[2])}
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.dks_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass

@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing: one process per GPU with ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in CPU
+tests).  The KernelSHAP path shards over instances with no exchange during compute; the single collective is an
+all-gather of the shap-value blocks (replaces ``DistributedExplainer.order_result`` + plasma gets,
+explainers/distributed.py:152-179)."""
+import os
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def is_distributed():
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return False
+    try:
+        dist = _dist()
+    except ImportError:  # pragma: no cover
+        return False
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rank():
+    return _dist().get_rank() if is_distributed() else 0
+
+
+def world_size():
+    return _dist().get_world_size() if is_distributed() else 1
+
+
+def visible_gpus():
+    """Number of CUDA devices this process can see (through libdks, without importing torch)."""
+    import ctypes
+    from . import _cabi
+    n = ctypes.c_int(0)
+    if _cabi.load().dks_device_count(ctypes.byref(n)) != 0:
+        return 0
+    return int(n.value)
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (RANK / WORLD_SIZE / MASTER_*)."""
+    import torch
+    dist = _dist()
+    if dist.is_initialized():
+        return
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend)
+
+
+def shard_bounds(n, world):
+    """Row range of every rank under the ``np.array_split`` rule: the first ``n % world`` ranks get one extra row."""
+    base, extra = divmod(n, world)
+    sizes = [base + 1 if r < extra else base for r in range(world)]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    return [(int(starts[r]), int(starts[r + 1])) for r in range(world)]
+
+
+def allgather_rows(local, counts):
+    """All-gather blocks ``local`` [C, n_r, G] (float64) whose row counts ``counts`` may differ by rank; returns the
+    concatenation [C, sum(counts), G] on every rank.  Blocks are padded to the largest count because the collective
+    needs equal sizes."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    C, _, G = local.shape
+    pad = max(counts)
+    backend = dist.get_backend()
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    send = torch.zeros((C, pad, G), dtype=torch.float64, device=device)
+    if local.shape[1]:
+        send[:, :local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
+    recv = torch.empty((world, C, pad, G), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy()
+    return np.concatenate([recv[r][:, :counts[r]] for r in range(world)], axis=1)

@@ -1,0 +1,167 @@
+"""Coalition plans: which subsets of the M varying feature groups are evaluated, and with what kernel weight.
+
+Host-side product code (the north star keeps host code in Python).  It follows the enumeration + sampling rule
+of ``shap.KernelExplainer.explain`` (shap==0.35.0; reached from the reference at explainers/kernel_shap.py:250/253,
+see SURVEY.md App. A.4 steps 5-9) and emits each coalition as one 64-bit word (bit k = k-th varying group
+present), the layout ``dks_set_shared_plan`` / ``dks_explain_*`` consume.
+
+The random part draws from a legacy ``numpy.random.RandomState`` -- or the global ``numpy.random`` module, the
+stream the reference seeds (kernel_shap.py:228, :744) -- with exactly the calls upstream makes (one vectorised
+``choice`` then one ``permutation(M)`` per draw), so a plan built here from a given stream state is the plan
+shap would have built from it.
+"""
+from math import comb
+
+import numpy as np
+
+MAX_GROUPS = 64
+
+
+def resolve_nsamples(M, nsamples="auto"):
+    """Rows an instance with ``M`` varying groups evaluates, and the size of the coalition space.
+
+    'auto' = 2M + 2048; with M <= 30 the request is capped at 2**M - 2 (all proper, non-empty subsets)."""
+    if nsamples in ("auto", None, 0):
+        nsamples = 2 * M + 2 ** 11
+    max_samples = 2 ** 30
+    if M <= 30:
+        max_samples = 2 ** M - 2
+        nsamples = min(nsamples, max_samples)
+    return int(nsamples), int(max_samples)
+
+
+def size_weights(M):
+    """Shapley-kernel mass of subset sizes 1..ceil((M-1)/2); sizes with a distinct complement size count twice."""
+    n_sizes = int(np.ceil((M - 1) / 2.0))
+    n_paired = int(np.floor((M - 1) / 2.0))
+    wv = np.array([(M - 1.0) / (s * (M - s)) for s in range(1, n_sizes + 1)])
+    wv[:n_paired] *= 2
+    wv /= wv.sum()
+    return wv, n_sizes, n_paired
+
+
+def _combination_bits(M, size):
+    """All size-``size`` subsets of range(M) as bit words, in itertools.combinations (lexicographic) order."""
+    from itertools import combinations
+    out = np.empty(comb(M, size), dtype=np.uint64)
+    for r, inds in enumerate(combinations(range(M), size)):
+        word = 0
+        for k in inds:
+            word |= 1 << k
+        out[r] = word
+    return out
+
+
+class CoalitionPlan:
+    """``zbits`` uint64[S], ``weights`` float64[S] in upstream row order, plus bookkeeping."""
+
+    def __init__(self, M, zbits, weights, nfixed, num_full_subsets, weight_left):
+        self.M = M
+        self.zbits = zbits
+        self.weights = weights
+        self.nfixed = nfixed
+        self.num_full_subsets = num_full_subsets
+        self.weight_left = weight_left
+
+    @property
+    def S(self):
+        return len(self.zbits)
+
+    def dense(self):
+        """[S, M] 0/1 matrix (upstream's ``maskMatrix``)."""
+        k = np.arange(self.M, dtype=np.uint64)
+        return ((self.zbits[:, None] >> k[None, :]) & np.uint64(1)).astype(np.uint8)
+
+
+def build_plan(M, nsamples="auto", rng=None):
+    """Plan for ``M`` varying groups.  ``rng``: RandomState-like (``choice``/``permutation``) or None for the global
+    ``numpy.random`` stream.  ``nsamples`` is the *request*; it is resolved with ``resolve_nsamples``."""
+    if not 2 <= M <= MAX_GROUPS:
+        raise ValueError(f"plans need 2 <= M <= {MAX_GROUPS} (got {M})")
+    if rng is None:
+        rng = np.random
+    S, _ = resolve_nsamples(M, nsamples)
+    full_mask = (1 << M) - 1
+    wv, n_sizes, n_paired = size_weights(M)
+
+    zbits = np.zeros(S, dtype=np.uint64)
+    weights = np.zeros(S, dtype=np.float64)
+    filled = 0
+
+    # --- subset sizes that fit entirely in the budget are enumerated, each followed by its complement ------
+    n_full = 0
+    budget = S
+    rem = wv.copy()
+    for size in range(1, n_sizes + 1):
+        paired = size <= n_paired
+        n_sub = float(comb(M, size)) * (2 if paired else 1)
+        if budget * rem[size - 1] / n_sub < 1.0 - 1e-8:
+            break
+        n_full += 1
+        budget -= n_sub
+        if rem[size - 1] < 1.0:
+            rem /= (1 - rem[size - 1])
+        w_row = wv[size - 1] / comb(M, size)
+        words = _combination_bits(M, size)
+        if paired:
+            w_row /= 2.0
+            block = np.empty(2 * len(words), dtype=np.uint64)
+            block[0::2] = words
+            block[1::2] = words ^ np.uint64(full_mask)
+        else:
+            block = words
+        zbits[filled:filled + len(block)] = block
+        weights[filled:filled + len(block)] = w_row
+        filled += len(block)
+
+    nfixed = filled
+    weight_left = 0.0
+    # --- the rest of the budget is sampled; repeated draws add to the weight of the first occurrence --------
+    if n_full != n_sizes:
+        left = S - filled
+        p = wv.copy()
+        p[:n_paired] /= 2  # a paired size yields two rows per draw
+        p = p[n_full:]
+        p /= p.sum()
+        picks = rng.choice(len(p), 4 * left, p=p)
+        first_row = {}
+        pos = 0
+        while left > 0 and pos < len(picks):
+            size = int(picks[pos]) + n_full + 1
+            pos += 1
+            members = rng.permutation(M)[:size]
+            word = 0
+            for k in members:
+                word |= 1 << int(k)
+            row = first_row.get(word)
+            fresh = row is None
+            if fresh:
+                first_row[word] = filled
+                zbits[filled] = word
+                weights[filled] = 1.0
+                filled += 1
+                left -= 1
+            else:
+                weights[row] += 1.0
+            if left > 0 and size <= n_paired:
+                if fresh:
+                    zbits[filled] = word ^ full_mask
+                    weights[filled] = 1.0
+                    filled += 1
+                    left -= 1
+                else:
+                    weights[row + 1] += 1.0  # the complement sits right after its original
+        weight_left = float(wv[n_full:].sum())
+        weights[nfixed:] *= weight_left / weights[nfixed:].sum()
+
+    return CoalitionPlan(M, zbits, weights, nfixed, n_full, weight_left)
+
+
+def pack_dense_plan(Z):
+    """[S, M] 0/1 matrix -> uint64[S] bit words (for feeding externally built plans to the engine)."""
+    Z = np.asarray(Z)
+    S, M = Z.shape
+    if M > MAX_GROUPS:
+        raise ValueError(f"at most {MAX_GROUPS} varying groups per coalition word")
+    k = np.arange(M, dtype=np.uint64)
+    return (Z.astype(np.uint64) << k[None, :]).sum(axis=1, dtype=np.uint64)

@@ -1,0 +1,133 @@
+/*
+ * dks.h -- C ABI of the B200-native KernelSHAP engine (libdks.so).
+ *
+ * The reference (alexcoca/DistributedKernelShap) has no FFI: its hot path is reached through a Python
+ * duck-typed slot, `KernelShap._explainer` (explainers/kernel_shap.py:774-788), whose object must offer
+ * `get_explanation(X, **kw)`, `.expected_value`, `.vector_out` (kernel_shap.py:789-790, :880-887).  The
+ * object the reference puts there is `KernelExplainerWrapper` (kernel_shap.py:217-261), a subclass of
+ * `shap.KernelExplainer` (shap==0.35.0, not vendored).  Each entry point below replaces one piece of
+ * that object; the Python binding a maintainer adds is in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success or a DKS_ERR_* code; dks_last_error() returns the
+ * message of the calling thread's last failure.  Plain pointers and sizes only -- no torch types.  A ctx
+ * is bound to one CUDA device, owns only its workspace, and is not thread-safe.  `*_dev` pointers are
+ * device memory owned by the caller (e.g. torch tensors); `*_host` pointers are host memory.  Work is
+ * enqueued on the ctx stream (dks_set_stream) and is asynchronous unless the function says it
+ * synchronises.  float64 at the boundary, like the reference.
+ */
+#ifndef DKS_H_
+#define DKS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKS_VERSION 100
+
+/* error codes */
+#define DKS_OK 0
+#define DKS_ERR_INVALID 1       /* bad argument / call order */
+#define DKS_ERR_CUDA 2          /* a CUDA runtime call failed (message has the CUDA error string) */
+#define DKS_ERR_UNSUPPORTED 3   /* valid request the engine does not implement (never a silent fallback) */
+#define DKS_ERR_PLAN_MISSING 4  /* an instance needs a coalition plan for an M that was not provided */
+#define DKS_ERR_NUMERIC 5       /* normal matrix not positive definite */
+
+/* model head applied to the linear scores z = W x + b   (replaces the opaque `predictor` callable,
+ * benchmarks/ray_pool.py:34; sklearn LogisticRegression.predict_proba per scripts/fit_adult_model.py:27) */
+#define DKS_ACT_IDENTITY 0      /* outputs = z (R outputs): regression / decision_function           */
+#define DKS_ACT_BINARY_LOGISTIC 1 /* R = 1, outputs [1 - s, s], s = sigmoid(kappa * z): kappa = 1 is the
+                                   * binary sigmoid, kappa = 2 the 2-class multinomial softmax([-z, z]) */
+#define DKS_ACT_SOFTMAX 2       /* R = C >= 2 scores, outputs softmax(z)                              */
+
+/* link (shap.common.convert_to_link; reference call sites kernel_shap.py:775, :949) */
+#define DKS_LINK_IDENTITY 0
+#define DKS_LINK_LOGIT 1
+
+/* which fused kernel evaluates the coalitions */
+#define DKS_KERNEL_AUTO 0
+#define DKS_KERNEL_SIMT 1       /* CUDA-core kernel (all shapes) */
+#define DKS_KERNEL_TCGEN05 2    /* tensor-core kernel: Z tile x background tile on tcgen05/TMEM */
+
+typedef struct dks_ctx dks_ctx;
+
+int dks_version(void);
+const char* dks_last_error(void);
+/* number of CUDA devices visible to the process (0 when there is none; never an error) */
+int dks_device_count(int* count);
+
+/* ---- lifetime ------------------------------------------------------------------------------------
+ * replaces KernelExplainerWrapper.__init__ (kernel_shap.py:225-229): one ctx per actor/GPU. */
+int dks_create(dks_ctx** out, int device);
+int dks_destroy(dks_ctx* ctx);
+/* `stream` is a cudaStream_t (0 = legacy default stream).  The ctx creates its own stream by default. */
+int dks_set_stream(dks_ctx* ctx, void* stream);
+int dks_synchronize(dks_ctx* ctx);
+
+/* ---- fit: shap.common.DenseData + KernelExplainer.__init__ (reached from kernel_shap.py:229) --------
+ * background [N x D] row-major float64, optional weights [N] (NULL = uniform; normalised to sum 1). */
+int dks_set_background(dks_ctx* ctx, const double* bg_host, int N, int D, const double* weights_host);
+/* feature groups in CSR form: group g owns columns group_cols[group_offsets[g] .. group_offsets[g+1]).
+ * Every column must belong to exactly one group (DenseData asserts the sizes add up to D). */
+int dks_set_groups(dks_ctx* ctx, const int32_t* group_offsets, const int32_t* group_cols, int G);
+/* linear scores z = W x + b with W [R x D] row-major, b [R]; head per DKS_ACT_*; kappa used by
+ * DKS_ACT_BINARY_LOGISTIC only.  scalar_out != 0 marks a predictor returning a 1-D array (vector_out False). */
+int dks_set_model(dks_ctx* ctx, const double* W_host, const double* b_host, int R, int activation, double kappa,
+                  int scalar_out);
+int dks_set_link(dks_ctx* ctx, int link);
+/* runs the fit kernels (grouped background scores, fnull = sum_j w_j f(bg_j), link(fnull)); synchronises. */
+int dks_fit(dks_ctx* ctx);
+int dks_num_outputs(dks_ctx* ctx, int* C);
+/* fnull[C] and expected_value[C] = link(fnull)  (KernelExplainer.fnull / .expected_value) */
+int dks_get_fnull(dks_ctx* ctx, double* fnull_host, double* expected_value_host);
+/* model outputs f(X) [n x C] for host rows (used to check the extracted model against the callable). */
+int dks_predict_host(dks_ctx* ctx, const double* X_host, int n, double* out_host);
+
+/* ---- coalition plans: the enumeration/sampling part of KernelExplainer.explain ----------------------
+ * nsamples request shared by all instances: 0 = 'auto' (2M + 2048); capped per instance at 2^M - 2 (M<=30). */
+int dks_set_nsamples(dks_ctx* ctx, int nsamples);
+/* S an instance with M varying groups evaluates under the current request (upstream rule). */
+int dks_effective_nsamples(dks_ctx* ctx, int M, int* S);
+/* one plan shared by every instance with M varying groups: zbits [S] (bit k = k-th varying group present),
+ * w [S] kernel weights, in upstream row order.  Copies to the device and factors the normal matrix. */
+int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, const double* w_host);
+int dks_clear_plans(dks_ctx* ctx);
+int dks_has_shared_plan(dks_ctx* ctx, int M, int* present);
+
+/* ---- explain: KernelExplainer.shap_values (reached from kernel_shap.py:250/253) ---------------------
+ * Stage 1 (dks_prepare_*): per instance, grouped contributions W_g x_g, f(x), link(f(x)) - link(fnull),
+ * varying_groups() bit-mask and M.  X is [n x D] row-major float64. */
+int dks_prepare_host(dks_ctx* ctx, const double* X_host, int n);
+int dks_prepare_dev(dks_ctx* ctx, const double* X_dev, int n);
+/* after prepare: hist[m] = number of instances with M == m, m in [0, G]; synchronises. */
+int dks_get_m_histogram(dks_ctx* ctx, int32_t* hist_host);
+/* after prepare: per-instance M and varying bit-mask (debug / tests); synchronises. */
+int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host);
+
+/* Stage 2: evaluate coalitions + solve.  phi is [C x n x G] float64 (one [n x G] slab per model output,
+ * the list-of-arrays layout KernelExplainer.shap_values returns).
+ * Plans: ext_zbits/ext_w == NULL -> shared plans (dks_set_shared_plan) looked up by each instance's M;
+ * otherwise per-instance plans [n x ext_stride] (row i holds the S_i = dks_effective_nsamples(M_i) rows of
+ * instance i), device pointers for _dev and host pointers for _host. */
+int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev, const double* ext_w_dev,
+                    int ext_stride);
+/* convenience: prepare + explain from/to host memory; H2D, kernels, D2H; synchronises.  This is the call a
+ * non-torch host (ctypes / cgo) makes and the one bench.py's end-to-end number goes through. */
+int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
+                     const double* ext_w_host, int ext_stride);
+/* status of the last explain (checked after synchronisation): 0 ok, DKS_ERR_PLAN_MISSING, DKS_ERR_NUMERIC;
+ * *detail = the offending M / instance index. */
+int dks_last_status(dks_ctx* ctx, int* detail);
+
+/* ---- knobs / introspection ---------------------------------------------------------------------- */
+int dks_set_kernel(dks_ctx* ctx, int kernel);       /* DKS_KERNEL_* */
+int dks_kernel_launches(dks_ctx* ctx, int64_t* count); /* kernels launched by this ctx so far */
+/* device-time of the last explain's stages in ms (CUDA events on the ctx stream): [0] prepare, [1] fused
+ * coalition kernel, [2] total; synchronises. */
+int dks_last_timings(dks_ctx* ctx, float* ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKS_H_ */

@@ -1,0 +1,211 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.  Tolerance: 1e-5 relative
+to the largest |phi| of the instance (BASELINE.json north_star: "within 1e-5 relative"); additivity to 1e-8."""
+import numpy as np
+import pytest
+
+from conftest import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _oracle(prob, link="logit", predict="predict_proba"):
+    from oracle.shap_kernel_oracle import DenseData, KernelExplainerOracle
+    args = (prob["groups"],) + ((prob["weights"],) if prob["weights"] is not None else ())
+    dd = DenseData(prob["bg"], prob["group_names"], *args)
+    return KernelExplainerOracle(getattr(prob["clf"], predict), dd, link=link, record_plans=True)
+
+
+def _engine(prob, link="logit", predict="predict_proba", **kw):
+    from distributedkernelshap_b200.data import DenseData
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    args = (prob["groups"],) + ((prob["weights"],) if prob["weights"] is not None else ())
+    dd = DenseData(prob["bg"], prob["group_names"], *args)
+    return GpuKernelExplainer(getattr(prob["clf"], predict), dd, link=link, **kw)
+
+
+def _compare(got, want, tol=TOL):
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        assert rel_err(g, w) < tol, rel_err(g, w)
+
+
+@pytest.mark.parametrize("link", ["logit", "identity"])
+@pytest.mark.parametrize("kappa", [2.0, 1.0])
+def test_full_enumeration_matches_oracle(link, kappa):
+    """S >= 2^M - 2: the plan is RNG-free; GPU and oracle build it independently."""
+    prob = make_problem(seed=1, n=16, N=12, widths=(1, 1, 3, 2, 1, 2), kappa=kappa)
+    orc, eng = _oracle(prob, link), _engine(prob, link)
+    want = orc.shap_values(prob["X"], nsamples=10000, l1_reg=False)
+    got = eng.shap_values(prob["X"], nsamples=10000, l1_reg=False)
+    _compare(got, want)
+    np.testing.assert_allclose(eng.expected_value, orc.expected_value, rtol=1e-12)
+
+
+def test_expected_value_and_additivity():
+    prob = make_problem(seed=2, n=32, N=20, widths=(1, 1, 1, 4, 3, 1, 1, 2), weights=True)
+    eng = _engine(prob, "logit")
+    sv = eng.shap_values(prob["X"], nsamples=150, l1_reg=False)
+    fx = prob["clf"].predict_proba(prob["X"])
+    for c in range(2):
+        total = np.log(fx[:, c] / (1 - fx[:, c])) - eng.expected_value[c]
+        np.testing.assert_allclose(sv[c].sum(axis=1), total, rtol=1e-8, atol=1e-8)
+    # two-class antisymmetry
+    np.testing.assert_allclose(sv[0], -sv[1], rtol=0, atol=1e-12)
+
+
+def test_external_per_instance_plans_match_oracle():
+    """Sampled plans: the oracle draws one plan per instance from the advancing MT19937 stream (what shap does);
+    the very same plans are fed to the GPU."""
+    prob = make_problem(seed=3, n=24, N=16, widths=(1, 1, 1, 1, 3, 2, 1, 2, 1, 4, 1, 1))
+    orc, eng = _oracle(prob), _engine(prob)
+    np.random.seed(0)
+    want = orc.shap_values(prob["X"], nsamples=500, l1_reg=False)
+    plans = [(Z, w) for (_, Z, w) in orc.plans]
+    got = eng.shap_values(prob["X"], nsamples=500, l1_reg=False, plans=plans)
+    _compare(got, want)
+
+
+def test_shared_plan_matches_oracle_fed_the_same_plan():
+    from distributedkernelshap_b200.plan import build_plan
+    prob = make_problem(seed=4, n=20, N=25, widths=(1,) * 4 + (3, 2, 2, 1, 5, 1), weights=True)
+    orc = _oracle(prob)
+    np.random.seed(11)
+    eng = _engine(prob)
+    got = eng.shap_values(prob["X"], nsamples=300, l1_reg=False)
+    np.random.seed(11)  # the engine drew its M=10 plan from this state
+    plan = build_plan(10, 300)
+    want = [np.zeros_like(g) for g in got]
+    for i in range(prob["X"].shape[0]):
+        phi = orc.explain(prob["X"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=300, l1_reg=False)
+        for c in range(2):
+            want[c][i] = phi[:, c]
+    _compare(got, want)
+
+
+def test_non_varying_groups_and_degenerate_M():
+    prob = make_problem(seed=5, n=10, N=8, widths=(1, 2, 1, 3, 1), constant_groups=(1, 3))
+    X = prob["X"]
+    prob["bg"][:] = prob["bg"][0]                            # constant background: a group varies iff x differs from it
+    X[1] = prob["bg"][0]                                     # M = 0
+    X[2] = prob["bg"][0]; X[2, 0] += 1.0                     # M = 1
+    orc, eng = _oracle(prob), _engine(prob)
+    want = orc.shap_values(X, nsamples=100, l1_reg=False)
+    got = eng.shap_values(X, nsamples=100, l1_reg=False)
+    _compare(got, want)
+    assert np.all(got[1][:, 1] == 0) and np.all(got[1][:, 3] == 0)   # non-varying groups get exactly 0
+    assert np.all(got[1][1] == 0)
+    M, mask = eng.varying(X)
+    assert M[1] == 0 and M[2] == 1
+    want_M = [len(orc.varying_groups(X[i:i + 1])) for i in range(X.shape[0])]
+    assert list(M) == want_M
+
+
+def test_varying_groups_isclose_rule():
+    """np.isclose(x, bg, rtol=1e-5, atol=1e-8): differences below the tolerance do not make a group vary."""
+    prob = make_problem(seed=6, n=6, N=5, widths=(1, 1, 2))
+    prob["bg"][:, 0] = 3.0
+    prob["X"][:, 0] = [3.0, 3.0 + 2e-5, 3.0 + 4e-5, 3.0 - 2e-5, 3.0 + 3.1e-5, 3.0 - 3.1e-5]
+    orc, eng = _oracle(prob), _engine(prob)
+    M, mask = eng.varying(prob["X"])
+    for i in range(6):
+        vi = orc.varying_groups(prob["X"][i:i + 1])
+        assert sorted(np.nonzero([(int(mask[i]) >> g) & 1 for g in range(3)])[0]) == sorted(vi), i
+
+
+def test_identity_head_closed_form():
+    """Affine model + identity link: phi_g = sum_{k in g} w_k (x_k - E_bg[bg_k]) exactly."""
+    prob = make_problem(seed=7, n=12, N=9, widths=(1, 2, 1, 3, 1, 1, 2), weights=True)
+    eng = _engine(prob, link="identity", predict="decision_function")
+    orc = _oracle(prob, link="identity", predict="decision_function")
+    got = eng.shap_values(prob["X"], nsamples=64, l1_reg=False)
+    assert isinstance(got, np.ndarray) and got.shape == (12, 7) and not eng.vector_out
+    wb = prob["weights"] / prob["weights"].sum()
+    coef = prob["clf"].coef_[0]
+    for g, cols in enumerate(prob["groups"]):
+        closed = ((prob["X"][:, cols] - (wb[:, None] * prob["bg"][:, cols]).sum(0)) * coef[cols]).sum(1)
+        np.testing.assert_allclose(got[:, g], closed, rtol=1e-9, atol=1e-10)
+    np.random.seed(0)
+    want = orc.shap_values(prob["X"], nsamples=64, l1_reg=False)
+    assert rel_err(got, want) < 1e-8
+
+
+def test_adult_shape_shared_plan_parity_and_sharding_invariance():
+    """BASELINE config[1] shape (D=49, 12 groups, bg=100, nsamples=2048) on a subset of instances."""
+    from distributedkernelshap_b200.datasets import adult_like
+    from distributedkernelshap_b200.plan import build_plan
+    from oracle.shap_kernel_oracle import DenseData, KernelExplainerOracle
+    d = adult_like(n_explain=64)
+    prob = dict(X=d["X_explain"], bg=d["background"], groups=d["groups"], group_names=d["group_names"],
+                clf=d["predictor"], weights=None)
+    np.random.seed(0)
+    eng = _engine(prob)
+    got = eng.shap_values(prob["X"], nsamples=2048, l1_reg=False)
+    M, _ = eng.varying(prob["X"])
+    np.random.seed(0)
+    plans = {}
+    for m in sorted(set(int(v) for v in M if v >= 2)):   # the engine builds missing plans in increasing M
+        plans[m] = build_plan(m, 2048)
+    orc = KernelExplainerOracle(d["predictor"].predict_proba, DenseData(prob["bg"], prob["group_names"], prob["groups"]),
+                                link="logit")
+    for i in range(0, 64, 4):
+        p = plans[int(M[i])]
+        phi = orc.explain(prob["X"][i:i + 1], plan=(p.dense(), p.weights), nsamples=2048, l1_reg=False)
+        assert rel_err(got[1][i], phi[:, 1]) < TOL
+    # explaining in two halves gives the same rows (replaces order_result, distributed.py:156-179)
+    a = eng.shap_values(prob["X"][:30], nsamples=2048, l1_reg=False)
+    b = eng.shap_values(prob["X"][30:], nsamples=2048, l1_reg=False)
+    np.testing.assert_array_equal(np.concatenate([a[1], b[1]]), got[1])
+
+
+def test_l1_reg_is_refused_not_ignored():
+    prob = make_problem(seed=8, n=4, N=6, widths=(1,) * 16)
+    eng = _engine(prob)
+    with pytest.raises(NotImplementedError):
+        eng.shap_values(prob["X"], nsamples=200)          # l1_reg='auto' would trigger: 200 / (2^16 - 2) < 0.2
+    with pytest.raises(NotImplementedError):
+        eng.shap_values(prob["X"], nsamples=200, l1_reg="num_features(3)")
+    eng.shap_values(prob["X"], nsamples=200, l1_reg=False)
+
+
+def test_model_mismatch_is_refused():
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from distributedkernelshap_b200.predictors import LinearModelSpec
+    prob = make_problem(seed=9)
+    with pytest.raises(TypeError):
+        GpuKernelExplainer(lambda X: X.sum(1), prob["bg"])
+
+    class Liar:
+        coef_ = prob["clf"].coef_
+        intercept_ = prob["clf"].intercept_
+
+        def predict_proba(self, X):
+            return prob["clf"].predict_proba(X) ** 2
+    with pytest.raises(ValueError):
+        GpuKernelExplainer(Liar().predict_proba, prob["bg"])
+    assert LinearModelSpec(prob["clf"].coef_, prob["clf"].intercept_, "binary_logistic", 2.0).n_outputs == 2
+
+
+def test_kernelshap_api_end_to_end():
+    """The reference's own call sequence (benchmarks/ray_pool.py:34-37, :73)."""
+    from distributedkernelshap_b200.datasets import adult_like
+    from distributedkernelshap_b200.explainers.kernel_shap import KernelShap
+    d = adult_like(n_explain=40)
+    data = d["data"]
+    explainer = KernelShap(d["predictor"].predict_proba, link="logit", feature_names=d["group_names"], seed=0)
+    explainer.fit(data["background"]["X"]["preprocessed"], group_names=d["group_names"], groups=d["groups"])
+    explanation = explainer.explain(d["X_explain"], silent=True, nsamples=2048, l1_reg=False)
+    sv = explanation.shap_values
+    assert len(sv) == 2 and sv[0].shape == (40, 12)
+    raw = explanation.raw["raw_prediction"]
+    np.testing.assert_allclose(sv[1].sum(1) + explanation.expected_value[1], raw[:, 1], rtol=1e-7, atol=1e-7)
+    # distributed_opts: mini-batches of 10 rows through DistributedExplainer give the same values
+    dist = KernelShap(d["predictor"].predict_proba, link="logit", feature_names=d["group_names"], seed=0,
+                      distributed_opts={"n_cpus": 1, "batch_size": 10, "actor_cpu_fraction": 1.0})
+    dist.fit(data["background"]["X"]["preprocessed"], group_names=d["group_names"], groups=d["groups"])
+    sv2 = dist.explain(d["X_explain"], silent=True, nsamples=2048, l1_reg=False).shap_values
+    np.testing.assert_allclose(sv2[1], sv[1], rtol=0, atol=1e-12)
+    js = explanation.to_json()
+    assert '"shap_values"' in js
