@@ -75,7 +75,7 @@ def allgather_rows(local, counts):
     send = torch.zeros((C, pad, G), dtype=torch.float64, device=device)
     if local.shape[1]:
         send[:, :local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
-    recv = torch.empty((world, C, pad, G), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(recv, send)
-    recv = recv.cpu().numpy()
+    recv = torch.empty(world * send.numel(), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send.view(-1))
+    recv = recv.view(world, C, pad, G).cpu().numpy()
     return np.concatenate([recv[r][:, :counts[r]] for r in range(world)], axis=1)
