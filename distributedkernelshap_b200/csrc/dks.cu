@@ -120,6 +120,15 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     if (S_cap < 2) S_cap = 2;
     p.S_cap = S_cap;
 
+    if (ctx->dbg_i >= 0) {   // debug dump of one instance's accumulator tile (tcgen05 kernel only)
+        int rows = S_cap, cols = dks::tc_npad(ctx->N);
+        if (rows != ctx->dbg_rows || cols != ctx->dbg_cols) {
+            TRY(dev_alloc(&ctx->dbg_T, (size_t)rows * cols));
+            ctx->dbg_rows = rows; ctx->dbg_cols = cols;
+        }
+        CUDA_TRY(cudaMemsetAsync(ctx->dbg_T, 0, sizeof(float) * rows * cols, ctx->stream));
+    }
+
     int kernel = ctx->kernel_choice;
     if (kernel == DKS_KERNEL_AUTO) kernel = dks::tc_supported(ctx, p) ? DKS_KERNEL_TCGEN05 : DKS_KERNEL_SIMT;
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -216,6 +225,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_hist); dev_free(&ctx->d_status); dev_free(&ctx->d_phi); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
+    dev_free(&ctx->dbg_T);
     for (void* p : ctx->plan_allocs) cudaFree(p);
     dks::tc_release(ctx);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -247,7 +257,9 @@ int dks_set_background(dks_ctx* ctx, const double* bg_host, int N, int D, const 
     ctx->N = N; ctx->D = D;
     ctx->h_bg.assign(bg_host, bg_host + (size_t)N * D);
     ctx->h_wbg.assign(N, 1.0 / N);
+    ctx->uniform_w = true;
     if (weights_host) {
+        for (int j = 1; j < N; ++j) if (weights_host[j] != weights_host[0]) ctx->uniform_w = false;
         double sum = 0;
         for (int j = 0; j < N; ++j) sum += weights_host[j];
         REQUIRE(sum > 0, "dks_set_background: weights must have a positive sum");
@@ -563,6 +575,23 @@ int dks_last_timings(dks_ctx* ctx, float* ms3) {
     CUDA_TRY(cudaEventElapsedTime(&ms3[0], ctx->ev[0], ctx->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&ms3[1], ctx->ev[2], ctx->ev[3]));
     CUDA_TRY(cudaEventElapsedTime(&ms3[2], ctx->ev[0], ctx->ev[3]));
+    return DKS_OK;
+}
+
+int dks_debug_score_dump(dks_ctx* ctx, int instance) {
+    REQUIRE(ctx, "null ctx");
+    ctx->dbg_i = instance;
+    return DKS_OK;
+}
+
+int dks_debug_get_scores(dks_ctx* ctx, float* out_host, int max_floats, int* rows, int* cols) {
+    BIND(ctx);
+    REQUIRE(ctx->dbg_T && out_host && rows && cols, "dks_debug_get_scores: no dump available");
+    *rows = ctx->dbg_rows; *cols = ctx->dbg_cols;
+    REQUIRE((long long)ctx->dbg_rows * ctx->dbg_cols <= max_floats, "dks_debug_get_scores: buffer too small");
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->dbg_T, sizeof(float) * ctx->dbg_rows * ctx->dbg_cols, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DKS_OK;
 }
 

@@ -71,6 +71,9 @@ struct dks_ctx {
     bool fitted = false;
     int kernel_choice = DKS_KERNEL_AUTO;
     int nsamples_req = 0;
+    bool uniform_w = true;      // background weights all equal
+    float* dbg_T = nullptr;     // debug dump of the tcgen05 score tile of instance dbg_i ([dbg_rows][dbg_cols])
+    int dbg_i = -1, dbg_rows = 0, dbg_cols = 0;
 
     // host copies
     std::vector<double> h_bg, h_wbg, h_W, h_b;

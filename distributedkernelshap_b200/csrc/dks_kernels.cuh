@@ -223,9 +223,9 @@ __global__ void prep_instance_kernel(const double* __restrict__ XW, const unsign
 
 // A = E^T diag(w) E for k,l < M-1 (symmetric, row-major nA x nA), built warp-per-entry
 __device__ inline void wls_build_normal(const uint64_t* __restrict__ zp, const double* __restrict__ wp, int S, int M,
-                                        double* A) {
+                                        double* A, int warp, int nwarps) {
     const int nA = M - 1, L = M - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int npairs = nA * (nA + 1) / 2;
     for (int pr = warp; pr < npairs; pr += nwarps) {
         int k = 0, rem = pr;
@@ -265,9 +265,9 @@ __device__ inline bool wls_cholesky_warp(double* A, int nA) {
 
 // rhs[k] = sum_s w_s e_sk (y_s - z_sL * delta), warp-per-k
 __device__ inline void wls_build_rhs(const uint64_t* __restrict__ zp, const double* __restrict__ wp,
-                                     const double* ys, int S, int M, double delta, double* rhs) {
+                                     const double* ys, int S, int M, double delta, double* rhs, int warp, int nwarps) {
     const int nA = M - 1, L = M - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     for (int k = warp; k < nA; k += nwarps) {
         double acc = 0;
         for (int s = lane; s < S; s += 32) {
@@ -316,7 +316,7 @@ __global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double*
     extern __shared__ double sm_d[];
     double* A = sm_d;
     const int nA = M - 1;
-    wls_build_normal(z, w, S, M, A);
+    wls_build_normal(z, w, S, M, A, threadIdx.x >> 5, blockDim.x >> 5);
     __syncthreads();
     if (threadIdx.x < 32) {
         bool ok = wls_cholesky_warp(A, nA);
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
             if (chol != nullptr) {
                 for (int idx = tid; idx < (M - 1) * (M - 1); idx += blockDim.x) sm.A[idx] = chol[idx];
             } else {
-                wls_build_normal(zp, wp, S, M, sm.A);
+                wls_build_normal(zp, wp, S, M, sm.A, threadIdx.x >> 5, blockDim.x >> 5);
                 __syncthreads();
                 if (tid < 32) {
                     bool ok = wls_cholesky_warp(sm.A, M - 1);
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
             }
             Lf = sm.A;
             const double delta = p.dlink[(size_t)i * C + 1];
-            wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs);
+            wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs, threadIdx.x >> 5, blockDim.x >> 5);
             __syncthreads();
             if (tid == 0) {
                 wls_solve_write(Lf, sm.rhs, M, delta, sm.vi, p.phi + slab + (size_t)i * G, 1.0);
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
             if (chol != nullptr) {
                 for (int idx = tid; idx < (M - 1) * (M - 1); idx += blockDim.x) sm.A[idx] = chol[idx];
             } else {
-                wls_build_normal(zp, wp, S, M, sm.A);
+                wls_build_normal(zp, wp, S, M, sm.A, threadIdx.x >> 5, blockDim.x >> 5);
                 __syncthreads();
                 if (tid < 32) {
                     bool ok = wls_cholesky_warp(sm.A, M - 1);
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
                 }
                 __syncthreads();
                 const double delta = p.dlink[(size_t)i * C + r];
-                wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs);
+                wls_build_rhs(zp, wp, sm.ys, S, M, delta, sm.rhs, threadIdx.x >> 5, blockDim.x >> 5);
                 __syncthreads();
                 if (tid == 0) wls_solve_write(Lf, sm.rhs, M, delta, sm.vi, p.phi + (size_t)r * slab + (size_t)i * G, 1.0);
             }

@@ -292,6 +292,19 @@ class GpuKernelExplainer:
         _cabi.check(self.lib.dks_last_timings(self._ctx, _cabi.ptr(out)))
         return {"prepare": float(out[0]), "coalitions": float(out[1]), "total": float(out[2])}
 
+    def debug_scores(self, X, instance, nsamples="auto"):
+        """Raw accumulator tile of the tcgen05 kernel for one instance: float32 [S_cap, Npad] of scaled masked scores
+        ``-kappa*log2(e) * score(s, j)`` (tests only)."""
+        _cabi.check(self.lib.dks_debug_score_dump(self._ctx, int(instance)))
+        try:
+            self.shap_values(X, nsamples=nsamples, l1_reg=False)
+            buf = np.zeros(1 << 22, dtype=np.float32)
+            rows, cols = C.c_int(0), C.c_int(0)
+            _cabi.check(self.lib.dks_debug_get_scores(self._ctx, _cabi.ptr(buf), buf.size, C.byref(rows), C.byref(cols)))
+        finally:
+            _cabi.check(self.lib.dks_debug_score_dump(self._ctx, -1))
+        return buf[:rows.value * cols.value].reshape(rows.value, cols.value).copy()
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self.lib.dks_destroy(self._ctx)

@@ -127,6 +127,13 @@ int dks_kernel_launches(dks_ctx* ctx, int64_t* count); /* kernels launched by th
  * coalition kernel, [2] total; synchronises. */
 int dks_last_timings(dks_ctx* ctx, float* ms3);
 
+/* ---- debugging aid for the tcgen05 kernel (tests only) ---------------------------------------------------
+ * dks_debug_score_dump(ctx, i): the next explains also write the raw accumulator tile of instance i (scaled masked
+ * scores T[s][j], float32 [rows x cols]); i < 0 switches it off.  dks_debug_get_scores copies the dump to the host
+ * (synchronises); rows/cols report its shape. */
+int dks_debug_score_dump(dks_ctx* ctx, int instance);
+int dks_debug_get_scores(dks_ctx* ctx, float* out_host, int max_floats, int* rows, int* cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,9 @@ def _engine(prob, link="logit", predict="predict_proba", **kw):
     return GpuKernelExplainer(getattr(prob["clf"], predict), dd, link=link, **kw)
 
 
+KERNELS = ["simt", "tcgen05"]
+
+
 def _compare(got, want, tol=TOL):
     assert len(got) == len(want)
     for g, w in zip(got, want):
@@ -32,21 +35,23 @@ def _compare(got, want, tol=TOL):
         assert rel_err(g, w) < tol, rel_err(g, w)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("link", ["logit", "identity"])
 @pytest.mark.parametrize("kappa", [2.0, 1.0])
-def test_full_enumeration_matches_oracle(link, kappa):
+def test_full_enumeration_matches_oracle(link, kappa, kernel):
     """S >= 2^M - 2: the plan is RNG-free; GPU and oracle build it independently."""
     prob = make_problem(seed=1, n=16, N=12, widths=(1, 1, 3, 2, 1, 2), kappa=kappa)
-    orc, eng = _oracle(prob, link), _engine(prob, link)
+    orc, eng = _oracle(prob, link), _engine(prob, link, kernel=kernel)
     want = orc.shap_values(prob["X"], nsamples=10000, l1_reg=False)
     got = eng.shap_values(prob["X"], nsamples=10000, l1_reg=False)
     _compare(got, want)
     np.testing.assert_allclose(eng.expected_value, orc.expected_value, rtol=1e-12)
 
 
-def test_expected_value_and_additivity():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_expected_value_and_additivity(kernel):
     prob = make_problem(seed=2, n=32, N=20, widths=(1, 1, 1, 4, 3, 1, 1, 2), weights=True)
-    eng = _engine(prob, "logit")
+    eng = _engine(prob, "logit", kernel=kernel)
     sv = eng.shap_values(prob["X"], nsamples=150, l1_reg=False)
     fx = prob["clf"].predict_proba(prob["X"])
     for c in range(2):
@@ -56,11 +61,12 @@ def test_expected_value_and_additivity():
     np.testing.assert_allclose(sv[0], -sv[1], rtol=0, atol=1e-12)
 
 
-def test_external_per_instance_plans_match_oracle():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_external_per_instance_plans_match_oracle(kernel):
     """Sampled plans: the oracle draws one plan per instance from the advancing MT19937 stream (what shap does);
     the very same plans are fed to the GPU."""
     prob = make_problem(seed=3, n=24, N=16, widths=(1, 1, 1, 1, 3, 2, 1, 2, 1, 4, 1, 1))
-    orc, eng = _oracle(prob), _engine(prob)
+    orc, eng = _oracle(prob), _engine(prob, kernel=kernel)
     np.random.seed(0)
     want = orc.shap_values(prob["X"], nsamples=500, l1_reg=False)
     plans = [(Z, w) for (_, Z, w) in orc.plans]
@@ -68,12 +74,13 @@ def test_external_per_instance_plans_match_oracle():
     _compare(got, want)
 
 
-def test_shared_plan_matches_oracle_fed_the_same_plan():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_shared_plan_matches_oracle_fed_the_same_plan(kernel):
     from distributedkernelshap_b200.plan import build_plan
     prob = make_problem(seed=4, n=20, N=25, widths=(1,) * 4 + (3, 2, 2, 1, 5, 1), weights=True)
     orc = _oracle(prob)
     np.random.seed(11)
-    eng = _engine(prob)
+    eng = _engine(prob, kernel=kernel)
     got = eng.shap_values(prob["X"], nsamples=300, l1_reg=False)
     np.random.seed(11)  # the engine drew its M=10 plan from this state
     plan = build_plan(10, 300)
@@ -85,13 +92,14 @@ def test_shared_plan_matches_oracle_fed_the_same_plan():
     _compare(got, want)
 
 
-def test_non_varying_groups_and_degenerate_M():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_non_varying_groups_and_degenerate_M(kernel):
     prob = make_problem(seed=5, n=10, N=8, widths=(1, 2, 1, 3, 1), constant_groups=(1, 3))
     X = prob["X"]
     prob["bg"][:] = prob["bg"][0]                            # constant background: a group varies iff x differs from it
     X[1] = prob["bg"][0]                                     # M = 0
     X[2] = prob["bg"][0]; X[2, 0] += 1.0                     # M = 1
-    orc, eng = _oracle(prob), _engine(prob)
+    orc, eng = _oracle(prob), _engine(prob, kernel=kernel)
     want = orc.shap_values(X, nsamples=100, l1_reg=False)
     got = eng.shap_values(X, nsamples=100, l1_reg=False)
     _compare(got, want)
@@ -132,7 +140,8 @@ def test_identity_head_closed_form():
     assert rel_err(got, want) < 1e-8
 
 
-def test_adult_shape_shared_plan_parity_and_sharding_invariance():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_adult_shape_shared_plan_parity_and_sharding_invariance(kernel):
     """BASELINE config[1] shape (D=49, 12 groups, bg=100, nsamples=2048) on a subset of instances."""
     from distributedkernelshap_b200.datasets import adult_like
     from distributedkernelshap_b200.plan import build_plan
@@ -141,7 +150,7 @@ def test_adult_shape_shared_plan_parity_and_sharding_invariance():
     prob = dict(X=d["X_explain"], bg=d["background"], groups=d["groups"], group_names=d["group_names"],
                 clf=d["predictor"], weights=None)
     np.random.seed(0)
-    eng = _engine(prob)
+    eng = _engine(prob, kernel=kernel)
     got = eng.shap_values(prob["X"], nsamples=2048, l1_reg=False)
     M, _ = eng.varying(prob["X"])
     np.random.seed(0)
@@ -209,3 +218,61 @@ def test_kernelshap_api_end_to_end():
     np.testing.assert_allclose(sv2[1], sv[1], rtol=0, atol=1e-12)
     js = explanation.to_json()
     assert '"shap_values"' in js
+
+
+def test_tcgen05_accumulator_tile_matches_numpy():
+    """The tensor-core contraction on its own: T[s][j] = scale * masked score, against float64 NumPy."""
+    from distributedkernelshap_b200.plan import build_plan
+    prob = make_problem(seed=12, n=5, N=37, widths=(1, 1, 3, 2, 1, 2, 1, 1, 4), weights=True)
+    np.random.seed(2)
+    eng = _engine(prob, kernel="tcgen05")
+    inst = 3
+    T = eng.debug_scores(prob["X"], inst, nsamples=300)
+    np.random.seed(2)
+    plan = build_plan(9, 300)
+    Z = plan.dense().astype(np.float64)
+    coef, b = prob["clf"].coef_[0], prob["clf"].intercept_[0]
+    x = prob["X"][inst]
+    XW = np.array([(x[g] * coef[g]).sum() for g in prob["groups"]])
+    BW = np.stack([(prob["bg"][:, g] * coef[g]).sum(1) for g in prob["groups"]], axis=1)      # [N, G]
+    score = b + BW.sum(1)
+    scale = -2.0 * np.log2(np.e)
+    want = scale * (score[None, :] + Z @ (XW[None, :] - BW).T)                               # [S, N]
+    assert T.shape[1] == 48 and T.shape[0] >= 300
+    np.testing.assert_allclose(T[:300, :37], want, rtol=0, atol=2e-5)
+    assert np.all(T[:300, 37:] == 0)
+
+
+def test_tcgen05_and_simt_kernels_agree_and_many_instances_per_cta():
+    """More instances than SMs (persistent CTAs walk several instances, odd tile counts: S = 2072 -> 17 tiles)."""
+    from distributedkernelshap_b200.datasets import adult_like
+    d = adult_like(n_explain=700)
+    prob = dict(X=d["X_explain"], bg=d["background"], groups=d["groups"], group_names=d["group_names"],
+                clf=d["predictor"], weights=None)
+    res = {}
+    for kernel in KERNELS:
+        np.random.seed(0)
+        eng = _engine(prob, kernel=kernel)
+        res[kernel] = eng.shap_values(prob["X"], l1_reg=False)          # nsamples='auto' = 2072
+    assert rel_err(res["tcgen05"][1], res["simt"][1]) < 2e-6
+
+
+def test_golden_fixtures_on_gpu():
+    import glob
+    import os
+    from distributedkernelshap_b200.predictors import LinearSoftmaxClassifier
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))):
+        g = np.load(path, allow_pickle=True)
+        groups = [list(map(int, x)) for x in g["groups"]]
+        clf = LinearSoftmaxClassifier(g["coef"], g["intercept"], multi_class=str(g["multi_class"]))
+        prob = dict(X=g["X"], bg=g["bg"], groups=groups, group_names=[f"g{i}" for i in range(len(groups))], clf=clf,
+                    weights=g["weights"])
+        for kernel in (KERNELS if len(groups) <= 15 else ["simt"]):
+            eng = _engine(prob, link=str(g["link"]), kernel=kernel)
+            plans = None if g["full"] else [(g["Z"][i], g["w"][i]) for i in range(g["X"].shape[0])]
+            got = eng.shap_values(g["X"], nsamples=int(g["nsamples"]), l1_reg=False, plans=plans)
+            for c in range(2):
+                assert rel_err(got[c], g["phi"][:, :, c]) < TOL, (path, kernel)
+            if g["full"]:
+                assert rel_err(got[1], g["phi_exact"][:, :, 1]) < TOL
+            np.testing.assert_allclose(eng.expected_value, g["expected_value"], rtol=1e-12)
