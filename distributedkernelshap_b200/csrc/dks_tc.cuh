@@ -6,11 +6,13 @@
 // (scale = -kappa*log2 e, so exp(-kappa*score) = 2^T).  Z is 0/1 and exact in bf16; Delta is split into three bf16
 // terms (hi/mid/lo, ~fp32-exact) and accumulated in fp32 in TMEM by three tcgen05.mma (M=128, N=Npad, K=16).
 // Warp roles of the persistent CTA (one per SM):
-//   warp 0      producer: builds the instance's B operand (Delta splits) and each tile's A operand (Z bits expanded
-//               to bf16 in registers, never read from HBM as a matrix) in shared memory, issues the MMAs;
-//   warps 4-11  epilogue, two groups of four warps = two TMEM accumulator buffers: tcgen05.ld the 128 x N scores,
-//               p1 = 1/(1+2^T), background-weighted sums, link -> y[s] (float64) in shared memory;
-//   warps 1-3   constrained WLS of the previous instance (float64) while the next one is being evaluated.
+//   warps 0-3   producer group (one thread per tile row / background row): builds the instance's B operand (Delta
+//               splits) and each tile's A operand (Z bits expanded to bf16 through a 256-entry byte LUT, never read
+//               from HBM as a matrix) in shared memory; thread 0 issues the MMAs;
+//   warps 4-19  epilogue, four groups of four warps = four TMEM accumulator buffers: tcgen05.ld the 128 x N scores,
+//               p1 = 1/(1+2^T), background-weighted sums (sum p1, sum p0) per coalition row -> shared memory;
+//   warps 20-23 WLS warpgroup, one instance behind (float64): y = link(ey) - link(fnull) per row folded into
+//               E^T W y, per-instance normal matrix when the plan is not shared, triangular solves, phi.
 // All hand-offs are mbarriers (tcgen05.commit for MMA completion); no __syncthreads in the steady state.
 #pragma once
 
@@ -25,9 +27,11 @@ constexpr int TILE_S = 128;      // coalitions per MMA tile (UMMA M)
 constexpr int KP = 16;           // K per split: up to 15 varying groups + the constant column
 constexpr int NSPLIT = 3;        // bf16 hi/mid/lo
 constexpr int MAX_NPAD = 128;    // background rows per accumulator buffer (TMEM columns)
-constexpr int N_EPI_WARPS = 8, N_WLS_WARPS = 3;
-constexpr int NTHREADS = 32 * (1 + N_WLS_WARPS + N_EPI_WARPS);
-constexpr int TMEM_COLS = 256;   // two accumulator buffers of 128 fp32 columns
+constexpr int N_PROD_WARPS = 4, N_EPI_WARPS = 16, N_WLS_WARPS = 4;
+constexpr int NTHREADS = 32 * (N_PROD_WARPS + N_EPI_WARPS + N_WLS_WARPS);
+constexpr int NBUF = 4;          // accumulator / A-tile buffers: two per epilogue group
+constexpr int TMEM_COLS = 512;   // four accumulator buffers of 128 fp32 columns
+constexpr float T_CLAMP = 60.f;  // 2^t is clamped at 2^60 so the product of two (1 + 2^t) stays finite in fp32
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -104,7 +108,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding tcgen05.ld; the registers are in/out operands so no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
 
 // shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)):
 // 8x16-byte core matrices; LBO = bytes between the two K-adjacent core matrices of one K=16 step, SBO = bytes
@@ -124,33 +135,38 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 
 // ---- shared memory carve-up ---------------------------------------------------------------------------------
 struct Smem {
-    uint64_t* bars;      // [8]: tmem_full[2], tmem_empty[2], ys_full[2], ys_empty[2]
+    uint64_t* bars;      // [12]: tmem_full[4], tmem_empty[4], inst_full[2], inst_empty[2]
     uint32_t* tmem_ptr;  // [1]
-    int* vi;             // [16] varying position -> group (producer warp only)
+    int* vi;             // [16] varying position -> group (producer group only)
     double* chol;        // [15*15]
     double* rhs;         // [16]
-    double* ys;          // [2][S_cap]
+    double* part;        // [N_WLS_WARPS][16] per-warp partial right-hand sides
+    float2* accs;        // [2][S_cap] (sum p1, sum p0) per coalition row, per instance parity
     float* wb;           // [MAX_NPAD] background weights
-    unsigned char* A;    // [2][128*KP*2]
+    uint4* lut;          // [256] byte -> eight bf16 (1.0 / 0.0)
+    unsigned char* A;    // [NBUF][128*KP*2]
     unsigned char* B;    // [2][NSPLIT][Npad*KP*2]
 };
 __host__ __device__ inline size_t smem_bytes(int S_cap, int Npad) {
-    return 128 /*bars + tmem ptr*/ + 2 * 16 * sizeof(int) + (15 * 15 + 16) * sizeof(double) + 2 * (size_t)S_cap * sizeof(double) +
-           MAX_NPAD * sizeof(float) + 2 * (size_t)TILE_S * KP * 2 + 2 * NSPLIT * (size_t)Npad * KP * 2 + 64;
+    return 128 /*bars + tmem ptr*/ + 16 * sizeof(int) + (15 * 15 + 16 + N_WLS_WARPS * 16) * sizeof(double) +
+           2 * (size_t)S_cap * sizeof(float2) + MAX_NPAD * sizeof(float) + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
+           2 * NSPLIT * (size_t)Npad * KP * 2 + 64;
 }
 __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
     Smem s;
     s.bars = reinterpret_cast<uint64_t*>(base);
-    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 64);
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 112);
     s.vi = reinterpret_cast<int*>(base + 128);
-    s.chol = reinterpret_cast<double*>(base + 128 + 2 * 16 * sizeof(int));
+    s.chol = reinterpret_cast<double*>(base + 128 + 16 * sizeof(int));
     s.rhs = s.chol + 15 * 15;
-    s.ys = s.rhs + 16;
-    s.wb = reinterpret_cast<float*>(s.ys + 2 * (size_t)S_cap);
+    s.part = s.rhs + 16;
+    s.accs = reinterpret_cast<float2*>(s.part + N_WLS_WARPS * 16);
+    s.wb = reinterpret_cast<float*>(s.accs + 2 * (size_t)S_cap);
     unsigned char* p = reinterpret_cast<unsigned char*>(s.wb + MAX_NPAD);
     p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    s.A = p;
-    s.B = p + 2 * (size_t)TILE_S * KP * 2;
+    s.lut = reinterpret_cast<uint4*>(p);
+    s.A = p + 256 * 16;
+    s.B = s.A + NBUF * (size_t)TILE_S * KP * 2;
     return s;
 }
 
@@ -182,26 +198,81 @@ __device__ __forceinline__ int tiles_of(const ExplainParams& p, int i, int& M, i
     return (S + TILE_S - 1) / TILE_S;
 }
 
+// p1 = 1/(1+2^t) and p0 = 2^t/(1+2^t) (no cancellation) summed over background rows.  Two elements share one
+// reciprocal: r = 1/((1+ua)(1+ub)), p1a = r(1+ub), p1b = r(1+ua)  -> 1.5 MUFU ops per element instead of 2.
+// UW: uniform background weights (plain sums).
+template <bool UW>
+__device__ __forceinline__ void consume_pair(float ta, float tb, float wa, float wb_, float& a1, float& a0) {
+    ta = fminf(ta, T_CLAMP);
+    tb = fminf(tb, T_CLAMP);
+    const float ua = ex2_approx(ta), ub = ex2_approx(tb);
+    const float da = 1.f + ua, db = 1.f + ub;
+    const float r = rcp_approx(da * db);
+    const float ra = r * db, rb = r * da;
+    if (UW) {
+        a1 += ra;
+        a1 += rb;
+        a0 = fmaf(ua, ra, a0);
+        a0 = fmaf(ub, rb, a0);
+    } else {
+        a1 = fmaf(wa, ra, a1);
+        a1 = fmaf(wb_, rb, a1);
+        a0 = fmaf(wa * ua, ra, a0);
+        a0 = fmaf(wb_ * ub, rb, a0);
+    }
+}
+
+template <bool UW>
+__device__ __forceinline__ void consume16(const float (&v)[16], const float* __restrict__ wb, float& acc1, float& acc0) {
+    float a1[2] = {0.f, 0.f}, a0[2] = {0.f, 0.f};
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 2)
+        consume_pair<UW>(v[jj], v[jj + 1], UW ? 1.f : wb[jj], UW ? 1.f : wb[jj + 1], a1[(jj >> 1) & 1], a0[(jj >> 1) & 1]);
+    acc1 += a1[0] + a1[1];
+    acc0 += a0[0] + a0[1];
+}
+
+// last, partially filled chunk: only the first n (< 16) columns are background rows; weights come from shared memory
+// (zero for the padding column that completes an odd pair)
+__device__ __forceinline__ void consume_tail(const float (&v)[16], const float* __restrict__ wb, int n, float& acc1,
+                                             float& acc0) {
+    float a1 = 0.f, a0 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 2)
+        if (jj < n) consume_pair<false>(v[jj], v[jj + 1], wb[jj], wb[jj + 1], a1, a0);
+    acc1 += a1;
+    acc0 += a0;
+}
+
+template <bool UW, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams tp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ExplainParams& p = tp.p;
     const int Npad = tp.Npad, N = p.N, G = p.G;
     Smem sm = carve(smem_raw, p.S_cap, Npad);
     uint64_t* tmem_full = sm.bars;
-    uint64_t* tmem_empty = sm.bars + 2;
-    uint64_t* ys_full = sm.bars + 4;
-    uint64_t* ys_empty = sm.bars + 6;
+    uint64_t* tmem_empty = sm.bars + NBUF;
+    uint64_t* inst_full = sm.bars + 2 * NBUF;
+    uint64_t* inst_empty = sm.bars + 2 * NBUF + 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t slab = (size_t)p.n * G;
 
     if (threadIdx.x == 0) {
-        mbar_init(&tmem_full[0], 1);  mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 128); mbar_init(&tmem_empty[1], 128);
-        mbar_init(&ys_full[0], 32 * N_EPI_WARPS); mbar_init(&ys_full[1], 32 * N_EPI_WARPS);
-        mbar_init(&ys_empty[0], 32 * N_WLS_WARPS); mbar_init(&ys_empty[1], 32 * N_WLS_WARPS);
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        mbar_init(&inst_full[0], 32 * N_EPI_WARPS); mbar_init(&inst_full[1], 32 * N_EPI_WARPS);
+        mbar_init(&inst_empty[0], 32 * N_WLS_WARPS); mbar_init(&inst_empty[1], 32 * N_WLS_WARPS);
         fence_barrier_init();
     }
-    for (int j = threadIdx.x; j < MAX_NPAD; j += blockDim.x) sm.wb[j] = j < N ? p.wbf[j] : 0.f;
+    // weights of the padded columns are zero; with uniform weights the sums stay unnormalised (weight 1)
+    for (int j = threadIdx.x; j < MAX_NPAD; j += blockDim.x) sm.wb[j] = j < N ? (UW ? 1.f : p.wbf[j]) : 0.f;
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        uint4 e;
+        e.x = ((b & 1) ? 0x00003F80u : 0u) | ((b & 2) ? 0x3F800000u : 0u);
+        e.y = ((b & 4) ? 0x00003F80u : 0u) | ((b & 8) ? 0x3F800000u : 0u);
+        e.z = ((b & 16) ? 0x00003F80u : 0u) | ((b & 32) ? 0x3F800000u : 0u);
+        e.w = ((b & 64) ? 0x00003F80u : 0u) | ((b & 128) ? 0x3F800000u : 0u);
+        sm.lut[b] = e;
+    }
     if (warp == 0) tmem_alloc(sm.tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -210,46 +281,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
 
     const uint32_t a_bytes = TILE_S * KP * 2, b_split_bytes = (uint32_t)Npad * KP * 2;
 
-    if (warp == 0) {
-        // =================================== producer / MMA issuer ===================================
+    if (warp < N_PROD_WARPS) {
+        // =================================== producer group / MMA issuer ===================================
+        const int ptid = threadIdx.x;                 // 0..127: tile row (A) and background row (B) of this thread
+        constexpr int PROD_THREADS = 32 * N_PROD_WARPS;
         const uint32_t idesc = make_idesc(Npad);
-        uint32_t g = 0;  // global tile counter of this CTA
-        int q = 0;       // instance ordinal of this CTA
-        for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
-            int M, S;
-            const int T = tiles_of(p, i, M, S);
-            if (T == 0) continue;
+
+        // B operand of instance i into slot `slot`: Delta splits, K-major core matrices [kc][j][8]; thread = row j
+        auto build_B = [&](int i, int M, int slot) {
             const uint64_t vm = p.vmask[i];
-            const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : p.plans[M].z;
-            // before touching B[q&1] / A buffers the MMAs that read them two tiles ago must be done
-            unsigned char* Bq = sm.B + (size_t)(q & 1) * NSPLIT * b_split_bytes;
-            if (g >= 1) {  // every MMA issued so far has completed => the A/B buffers it read are free
-                uint32_t u = (g - 1) >> 1;
-                mbar_wait(&tmem_full[(g - 1) & 1], u & 1, p.status);
+            unsigned char* Bq = sm.B + (size_t)slot * NSPLIT * b_split_bytes;
+            named_bar_sync(2, PROD_THREADS);            // previous readers of sm.vi are done
+            if (ptid < KP) {                            // thread k finds the k-th varying group
+                int cnt = 0, gsel = 0;
+                for (int gI = 0; gI < G; ++gI)
+                    if ((vm >> gI) & 1ull) { if (cnt == ptid) gsel = gI; ++cnt; }
+                sm.vi[ptid] = ptid < M ? gsel : 0;
             }
-            // ---- B operand of this instance: Delta splits, K-major core matrices [kc][j][8] ----
-            {
-                {   // lane k finds the k-th varying group
-                    int cnt = 0, gsel = 0;
-                    for (int gI = 0; gI < G; ++gI)
-                        if ((vm >> gI) & 1ull) { if (cnt == lane) gsel = gI; ++cnt; }
-                    __syncwarp();
-                    if (lane < KP) sm.vi[lane] = lane < M ? gsel : 0;
-                    __syncwarp();
-                }
-                int vi[KP];
+            named_bar_sync(2, PROD_THREADS);
+            const int j = ptid;
+            if (j < Npad) {
 #pragma unroll
-                for (int kk = 0; kk < KP; ++kk) vi[kk] = sm.vi[kk];
-                double xw[KP];
+                for (int kc = 0; kc < 2; ++kc) {
+                    float hi[8], mid[8], lo[8];
 #pragma unroll
-                for (int kk = 0; kk < KP; ++kk) xw[kk] = kk < M ? p.XW[(size_t)i * G + vi[kk]] : 0.0;
-                for (int j = lane; j < Npad; j += 32) {
-                    float hi[KP], mid[KP], lo[KP];
-#pragma unroll
-                    for (int kk = 0; kk < KP; ++kk) {
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const int kk = kc * 8 + k8;
                         double v = 0.0;
                         if (j < N) {
-                            if (kk < M) v = p.scale * (xw[kk] - tp.BW[(size_t)j * G + vi[kk]]);
+                            const int gk = sm.vi[kk];
+                            if (kk < M) v = p.scale * (p.XW[(size_t)i * G + gk] - tp.BW[(size_t)j * G + gk]);
                             else if (kk == M) v = p.scale * tp.scores[j];
                         }
                         float vf = (float)v;
@@ -257,45 +318,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                         float r1 = vf - h;
                         float m = __bfloat162float(__float2bfloat16_rn(r1));
                         float r2 = (r1 - m) + (float)(v - (double)vf);
-                        hi[kk] = h; mid[kk] = m; lo[kk] = r2;
+                        hi[k8] = h; mid[k8] = m; lo[k8] = r2;
                     }
-#pragma unroll
-                    for (int kc = 0; kc < 2; ++kc) {
-                        uint4 wh, wm, wl;
-                        wh.x = pack_bf16(hi[kc * 8 + 0], hi[kc * 8 + 1]); wh.y = pack_bf16(hi[kc * 8 + 2], hi[kc * 8 + 3]);
-                        wh.z = pack_bf16(hi[kc * 8 + 4], hi[kc * 8 + 5]); wh.w = pack_bf16(hi[kc * 8 + 6], hi[kc * 8 + 7]);
-                        wm.x = pack_bf16(mid[kc * 8 + 0], mid[kc * 8 + 1]); wm.y = pack_bf16(mid[kc * 8 + 2], mid[kc * 8 + 3]);
-                        wm.z = pack_bf16(mid[kc * 8 + 4], mid[kc * 8 + 5]); wm.w = pack_bf16(mid[kc * 8 + 6], mid[kc * 8 + 7]);
-                        wl.x = pack_bf16(lo[kc * 8 + 0], lo[kc * 8 + 1]); wl.y = pack_bf16(lo[kc * 8 + 2], lo[kc * 8 + 3]);
-                        wl.z = pack_bf16(lo[kc * 8 + 4], lo[kc * 8 + 5]); wl.w = pack_bf16(lo[kc * 8 + 6], lo[kc * 8 + 7]);
-                        const size_t off = (size_t)kc * Npad * 16 + (size_t)j * 16;
-                        *reinterpret_cast<uint4*>(Bq + 0 * b_split_bytes + off) = wh;
-                        *reinterpret_cast<uint4*>(Bq + 1 * b_split_bytes + off) = wm;
-                        *reinterpret_cast<uint4*>(Bq + 2 * b_split_bytes + off) = wl;
-                    }
+                    uint4 wh, wm, wl;
+                    wh.x = pack_bf16(hi[0], hi[1]); wh.y = pack_bf16(hi[2], hi[3]);
+                    wh.z = pack_bf16(hi[4], hi[5]); wh.w = pack_bf16(hi[6], hi[7]);
+                    wm.x = pack_bf16(mid[0], mid[1]); wm.y = pack_bf16(mid[2], mid[3]);
+                    wm.z = pack_bf16(mid[4], mid[5]); wm.w = pack_bf16(mid[6], mid[7]);
+                    wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
+                    wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
+                    const size_t off = (size_t)kc * Npad * 16 + (size_t)j * 16;
+                    *reinterpret_cast<uint4*>(Bq + 0 * b_split_bytes + off) = wh;
+                    *reinterpret_cast<uint4*>(Bq + 1 * b_split_bytes + off) = wm;
+                    *reinterpret_cast<uint4*>(Bq + 2 * b_split_bytes + off) = wl;
                 }
             }
-            // ---- tiles ----
+        };
+        // next instance of this CTA (after i) that has tiles; -1 if none
+        auto next_work = [&](int i, int& Mn) {
+            for (int i2 = i + gridDim.x; i2 < p.n; i2 += gridDim.x) {
+                int S2;
+                if (tiles_of(p, i2, Mn, S2) > 0) return i2;
+            }
+            return -1;
+        };
+
+        uint32_t g = 0;   // global tile counter of this CTA
+        int qb = 0;       // ordinal among the instances that have tiles (selects the B slot)
+        int built_for = -1;
+        for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
+            int M, S;
+            const int T = tiles_of(p, i, M, S);
+            if (T == 0) continue;
+            const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : p.plans[M].z;
+            if (g >= 1) {  // every MMA issued so far has completed => the A/B buffers it read are free
+                uint32_t u = (g - 1) / NBUF;
+                mbar_wait(&tmem_full[(g - 1) % NBUF], u & 1, p.status);
+            }
+            if (built_for != i) build_B(i, M, qb & 1);      // only the first instance; later ones are prefetched below
+            unsigned char* Bq = sm.B + (size_t)(qb & 1) * NSPLIT * b_split_bytes;
             for (int t = 0; t < T; ++t, ++g) {
-                const uint32_t buf = g & 1, u = g >> 1;
-                if (t > 0 && g >= 2) mbar_wait(&tmem_full[buf], (u - 1) & 1, p.status);  // A[buf] free (MMA g-2 done)
+                const uint32_t buf = g % NBUF, u = g / NBUF;
+                const int s = t * TILE_S + ptid;
+                uint32_t zz = 0;
+                if (s < S) zz = (uint32_t)(zp[s] & 0xFFFFull) | (1u << M);       // constant column carries score_j
+                if (g >= NBUF) mbar_wait(&tmem_full[buf], (u - 1) & 1, p.status);     // A[buf] free (MMA g-NBUF done)
                 unsigned char* Ab = sm.A + (size_t)buf * a_bytes;
-#pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    const int sl = lane + 32 * r4;
-                    const int s = t * TILE_S + sl;
-                    uint32_t zz = 0;
-                    if (s < S) zz = (uint32_t)(zp[s] & 0xFFFFull) | (1u << M);   // constant column carries score_j
-                    uint32_t w[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        w[c] = (((zz >> (2 * c)) & 1u) ? 0x00003F80u : 0u) | (((zz >> (2 * c + 1)) & 1u) ? 0x3F800000u : 0u);
-                    *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + sl * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + sl * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                }
+                *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + ptid * 16) = sm.lut[zz & 0xFFu];
+                *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + ptid * 16) = sm.lut[(zz >> 8) & 0xFFu];
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) {
+                named_bar_sync(2, PROD_THREADS);
+                if (ptid == 0) {
                     mbar_wait(&tmem_empty[buf], (u & 1) ^ 1, p.status);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(Ab), TILE_S * 16, 128);
@@ -307,103 +380,89 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                     }
                     umma_commit(&tmem_full[buf]);   // arrives when the three MMAs have completed
                 }
-                __syncwarp();
+                // prefetch: while the epilogue chews on this instance, build the next instance's B operand.  Its slot
+                // was last read by the previous instance; MMAs complete in order, so once this instance's first MMA
+                // (just issued) has completed, that slot is free.
+                if (t == 0) {
+                    int Mn;
+                    int inext = next_work(i, Mn);
+                    if (inext >= 0) {
+                        mbar_wait(&tmem_full[buf], u & 1, p.status);
+                        build_B(inext, Mn, (qb + 1) & 1);
+                        built_for = inext;
+                    }
+                }
             }
+            ++qb;
         }
-    } else if (warp >= 1 + N_WLS_WARPS) {
+    } else if (warp < N_PROD_WARPS + N_EPI_WARPS) {
         // =================================== epilogue ===================================
-        const int ew = warp - (1 + N_WLS_WARPS);      // 0..7
+        // 16 warps = 4 groups x 4 warps; group g4 drains accumulator buffer g4 (tiles with g % 4 == g4).  Four
+        // epilogue warps share each SM sub-partition, enough independent MUFU chains in flight to keep its XU busy.
+        const int ew = warp - N_PROD_WARPS;           // 0..15
         const int grp = ew >> 2;                      // accumulator buffer this group drains
         const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
         const int row_in_tile = quarter * 32 + lane;
-        const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
-        const float inv_n = 1.0f / (float)N;
+        const int nfull = N / 16;                     // accumulator chunks of 16 columns without padding
+        const int ntail = N - nfull * 16;             // background rows in the last, partial chunk
+        const int nchunks = nfull + (ntail ? 1 : 0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 128;
+
         uint32_t g = 0;
         int q = 0;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
             int M, S;
             const int T = tiles_of(p, i, M, S);
-            double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
-            // y buffer of ordinal q-2 must have been consumed by the WLS warps
-            mbar_wait(&ys_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
+            float2* accs = sm.accs + (size_t)(q & 1) * p.S_cap;
+            bool waited = false;
             for (int t = 0; t < T; ++t, ++g) {
-                if ((int)(g & 1) != grp) continue;
-                const uint32_t buf = g & 1, u = g >> 1;
-                mbar_wait(&tmem_full[buf], u & 1, p.status);
+                if ((int)(g % NBUF) != grp) continue;
+                const uint32_t u = g / NBUF;
+                const int s = t * TILE_S + row_in_tile;
+                mbar_wait(&tmem_full[grp], u & 1, p.status);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128;
                 float acc1 = 0.f, acc0 = 0.f;
-                for (int c0 = 0; c0 < Npad; c0 += 16) {
+                for (int c = 0; c < nchunks; ++c) {
                     float v[16];
-                    tmem_ld16(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (tp.dbg_T != nullptr && i == tp.dbg_i) {
-                        const int s = t * TILE_S + row_in_tile;
-                        if (s < p.S_cap)
-                            for (int jj = 0; jj < 16; ++jj) tp.dbg_T[(size_t)s * Npad + c0 + jj] = v[jj];
+                    tmem_ld16(taddr + c * 16, v);
+                    tmem_ld_wait(v);
+                    if (DBG) {
+                        if (i == tp.dbg_i && s < p.S_cap)
+                            for (int jj = 0; jj < 16; ++jj) tp.dbg_T[(size_t)s * Npad + c * 16 + jj] = v[jj];
                     }
-                    if (c0 + 16 <= N) {
-                        if (tp.uniform_w) {
-#pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) {
-                                float tt = fminf(v[jj], 120.f);
-                                float uu = ex2_approx(tt);
-                                float rr = rcp_approx(1.f + uu);
-                                acc1 += rr;
-                                acc0 = fmaf(uu, rr, acc0);
-                            }
-                        } else {
-#pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) {
-                                float tt = fminf(v[jj], 120.f);
-                                float uu = ex2_approx(tt);
-                                float rr = rcp_approx(1.f + uu);
-                                float wj = sm.wb[c0 + jj];
-                                acc1 = fmaf(wj, rr, acc1);
-                                acc0 = fmaf(wj, uu * rr, acc0);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            if (c0 + jj < N) {
-                                float tt = fminf(v[jj], 120.f);
-                                float uu = ex2_approx(tt);
-                                float rr = rcp_approx(1.f + uu);
-                                float wj = tp.uniform_w ? 1.f : sm.wb[c0 + jj];
-                                acc1 = fmaf(wj, rr, acc1);
-                                acc0 = fmaf(wj, uu * rr, acc0);
-                            }
-                        }
-                    }
+                    if (c < nfull) consume16<UW>(v, sm.wb + c * 16, acc1, acc0);
+                    else consume_tail(v, sm.wb + c * 16, ntail, acc1, acc0);
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[buf]);       // accumulator buffer may be overwritten
-                const int s = t * TILE_S + row_in_tile;
-                if (s < S) {
-                    double y;
-                    if (p.link == DKS_LINK_LOGIT) y = log((double)acc1 / (double)acc0) - lf1;
-                    else y = (double)(tp.uniform_w ? acc1 * inv_n : acc1) - f1;
-                    ys[s] = y;
+                mbar_arrive(&tmem_empty[grp]);       // accumulator buffer may be overwritten
+                if (!waited) {   // the row buffer of ordinal q-2 must have been consumed by the WLS warps
+                    mbar_wait(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
+                    waited = true;
                 }
+                if (s < S) accs[s] = make_float2(acc1, acc0);
             }
-            mbar_arrive(&ys_full[q & 1]);            // release-arrive: this thread's y values are published
+            if (!waited) mbar_wait(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
+            mbar_arrive(&inst_full[q & 1]);          // release-arrive: publishes this thread's rows
         }
     } else {
-        // =================================== WLS warps (float64) ===================================
-        const int ww = warp - 1;                      // 0..2
-        const int wtid = threadIdx.x - 32;            // 0..95
+        // =================================== WLS warpgroup (float64) ===================================
+        // per row: y = link(ey) - link(fnull) from the (sum p1, sum p0) pair, folded into E^T W y; then the
+        // triangular solves and phi.  Runs one instance behind the epilogue.
+        const int ww = warp - (N_PROD_WARPS + N_EPI_WARPS);                  // 0..3
+        const int wtid = threadIdx.x - 32 * (N_PROD_WARPS + N_EPI_WARPS);     // 0..127
+        constexpr int WLS_THREADS = 32 * N_WLS_WARPS;
+        const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
+        const double inv_n = 1.0 / (double)N;
         int cachedM = -1;
         int q = 0;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
             int M, S;
             const int T = tiles_of(p, i, M, S);
             const int C = p.C;
-            for (int idx = wtid; idx < C * G; idx += 32 * N_WLS_WARPS)
+            for (int idx = wtid; idx < C * G; idx += WLS_THREADS)
                 p.phi[(size_t)(idx / G) * slab + (size_t)i * G + idx % G] = 0.0;
-            mbar_wait(&ys_full[q & 1], (q >> 1) & 1, p.status);
-            const double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
             if (T == 0) {
+                mbar_wait(&inst_full[q & 1], (q >> 1) & 1, p.status);
                 if (M == 1) {
                     if (wtid < C) {
                         int gI = __ffsll((long long)p.vmask[i]) - 1;
@@ -415,35 +474,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                     if (missing) { atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING); p.status[1] = M; }
                     else { atomicCAS(&p.status[0], 0, DKS_ERR_INVALID); p.status[1] = i; }
                 }
-                mbar_arrive(&ys_empty[q & 1]);
+                mbar_arrive(&inst_empty[q & 1]);
                 continue;
             }
+            const int nA = M - 1, L = M - 1;
             const uint64_t* zp;
             const double* wp;
-            const double* chol = nullptr;
-            if (p.ext_z) { zp = p.ext_z + (size_t)i * p.ext_stride; wp = p.ext_w + (size_t)i * p.ext_stride; }
-            else { zp = p.plans[M].z; wp = p.plans[M].w; chol = p.plans[M].chol; }
-            const int nA = M - 1;
-            if (chol != nullptr) {
+            // normal matrix / its Cholesky factor: shared plans bring a precomputed factor; per-instance plans are
+            // factored here, overlapping the epilogue of the same instance
+            if (p.ext_z == nullptr) {
+                zp = p.plans[M].z; wp = p.plans[M].w;
+                const double* chol = p.plans[M].chol;
                 if (M != cachedM) {
-                    named_bar_sync(1, 32 * N_WLS_WARPS);
-                    for (int idx = wtid; idx < nA * nA; idx += 32 * N_WLS_WARPS) sm.chol[idx] = chol[idx];
+                    named_bar_sync(1, WLS_THREADS);
+                    for (int idx = wtid; idx < nA * nA; idx += WLS_THREADS) sm.chol[idx] = chol[idx];
                     cachedM = M;
                 }
             } else {
                 cachedM = -1;
-                named_bar_sync(1, 32 * N_WLS_WARPS);
+                zp = p.ext_z + (size_t)i * p.ext_stride;
+                wp = p.ext_w + (size_t)i * p.ext_stride;
+                named_bar_sync(1, WLS_THREADS);
                 wls_build_normal(zp, wp, S, M, sm.chol, ww, N_WLS_WARPS);
-                named_bar_sync(1, 32 * N_WLS_WARPS);
+                named_bar_sync(1, WLS_THREADS);
                 if (ww == 0) {
                     bool ok = wls_cholesky_warp(sm.chol, nA);
                     if (!ok && lane == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
                 }
             }
             const double delta = p.dlink[(size_t)i * C + 1];
-            wls_build_rhs(zp, wp, ys, S, M, delta, sm.rhs, ww, N_WLS_WARPS);
-            named_bar_sync(1, 32 * N_WLS_WARPS);
+            mbar_wait(&inst_full[q & 1], (q >> 1) & 1, p.status);
+            const float2* accs = sm.accs + (size_t)(q & 1) * p.S_cap;
+            double Tk[KP - 1];
+#pragma unroll
+            for (int k = 0; k < KP - 1; ++k) Tk[k] = 0.0;
+            for (int s = wtid; s < S; s += WLS_THREADS) {
+                const float2 a = accs[s];
+                const uint64_t zrow = zp[s];
+                const double wrow = wp[s];
+                double y;
+                if (p.link == DKS_LINK_LOGIT) y = log((double)a.x / (double)a.y) - lf1;
+                else y = (UW ? (double)a.x * inv_n : (double)a.x) - f1;
+                // fold the row into E^T W y:  e_k = z_k - z_L = (z_L ? -1 : 1) * z'_k with z' = z_L ? ~z : z
+                const bool zl = (zrow >> L) & 1ull;
+                double v = wrow * (y - (zl ? delta : 0.0));
+                const uint32_t zb = (uint32_t)(zl ? ~zrow : zrow);
+                if (zl) v = -v;
+#pragma unroll
+                for (int k = 0; k < KP - 1; ++k)
+                    if (k < nA && ((zb >> k) & 1u)) Tk[k] += v;
+            }
+#pragma unroll
+            for (int k = 0; k < KP - 1; ++k)
+                if (k < nA) {
+                    double r = warp_sum(Tk[k]);
+                    if (lane == 0) sm.part[ww * 16 + k] = r;
+                }
+            named_bar_sync(1, WLS_THREADS);
             if (wtid == 0) {
+                for (int k = 0; k < nA; ++k) {           // fixed summation order: deterministic results
+                    double acc = 0.0;
+                    for (int e = 0; e < N_WLS_WARPS; ++e) acc += sm.part[e * 16 + k];
+                    sm.rhs[k] = acc;
+                }
                 int vi[KP];
                 {
                     const uint64_t vm = p.vmask[i];
@@ -455,8 +548,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 const double* phi1 = p.phi + slab + (size_t)i * G;
                 for (int k = 0; k < M; ++k) { double v = phi1[vi[k]]; phi0[vi[k]] = (v == 0.0) ? 0.0 : -v; }
             }
-            named_bar_sync(1, 32 * N_WLS_WARPS);
-            mbar_arrive(&ys_empty[q & 1]);
+            named_bar_sync(1, WLS_THREADS);
+            mbar_arrive(&inst_empty[q & 1]);
         }
     }
 
@@ -488,10 +581,14 @@ inline int tc_launch(dks_ctx* ctx, const ExplainParams& p) {
     tp.dbg_T = ctx->dbg_T;
     tp.dbg_i = ctx->dbg_i;
     size_t smem = tc::smem_bytes(p.S_cap, tp.Npad);
-    cudaError_t e = cudaFuncSetAttribute(tc::explain_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(tc::TcParams) = nullptr;
+    const bool dbg = tp.dbg_T != nullptr && tp.dbg_i >= 0;
+    if (dbg) kern = tp.uniform_w ? tc::explain_tcgen05_kernel<true, true> : tc::explain_tcgen05_kernel<false, true>;
+    else kern = tp.uniform_w ? tc::explain_tcgen05_kernel<true, false> : tc::explain_tcgen05_kernel<false, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return DKS_ERR_CUDA;
     int grid = ctx->sm_count < p.n ? ctx->sm_count : p.n;
-    tc::explain_tcgen05_kernel<<<grid, tc::NTHREADS, smem, ctx->stream>>>(tp);
+    kern<<<grid, tc::NTHREADS, smem, ctx->stream>>>(tp);
     ctx->launches += 1;
     return DKS_OK;
 }
