@@ -79,8 +79,8 @@ def load(build_if_needed=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if build_if_needed and _build.is_stale() and _build.find_nvcc() is not None:
+    path = os.environ.get("DKS_LIB", _build.LIB_PATH)     # DKS_LIB: tuning variants built by scripts/build_variants.sh
+    if path == _build.LIB_PATH and build_if_needed and _build.is_stale() and _build.find_nvcc() is not None:
         _build.build_library()
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -m distributedkernelshap_b200.build` "

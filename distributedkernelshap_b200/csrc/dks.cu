@@ -436,16 +436,18 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     BIND(ctx);
     REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_shared_plan: M=%d out of [2,%d]", M, DKS_MAX_GROUPS);
     REQUIRE(S >= 1 && zbits_host && w_host, "dks_set_shared_plan: bad arguments");
-    uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr;
+    uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr; double* di = nullptr;
     CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S));
     CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S));
     CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
+    CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
     ctx->plan_allocs.push_back(dz); ctx->plan_allocs.push_back(dw); ctx->plan_allocs.push_back(dc);
+    ctx->plan_allocs.push_back(di);
     CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
-    size_t smem = sizeof(double) * (size_t)(M - 1) * (M - 1);
-    dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, ctx->d_status);
+    size_t smem = 2 * sizeof(double) * (size_t)(M - 1) * (M - 1);
+    dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, di, ctx->d_status);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
@@ -454,7 +456,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         return fail(DKS_ERR_NUMERIC, "dks_set_shared_plan: normal matrix of the M=%d plan is not positive definite", M);
     PlanDev pd;
     memset(&pd, 0, sizeof(pd));
-    pd.z = dz; pd.w = dw; pd.chol = dc; pd.S = S;
+    pd.z = dz; pd.w = dw; pd.chol = dc; pd.ainv = di; pd.S = S;
     ctx->h_plans[M] = pd;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -16,7 +16,7 @@ struct PlanDev {
     const uint64_t* z;   // [S] coalition bits in upstream row order
     const double* w;     // [S] kernel weights
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
-    const float* ainv;   // reserved
+    const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
     int S;
     int pad;
 };

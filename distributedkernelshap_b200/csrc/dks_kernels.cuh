@@ -312,7 +312,7 @@ __device__ inline void wls_solve_write(const double* Lf, double* rhs, int M, dou
 
 // factor the normal matrix of a shared plan once (dks_set_shared_plan): one CTA
 __global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int S, int M,
-                                   double* __restrict__ chol, int* __restrict__ status) {
+                                   double* __restrict__ chol, double* __restrict__ ainv, int* __restrict__ status) {
     extern __shared__ double sm_d[];
     double* A = sm_d;
     const int nA = M - 1;
@@ -324,6 +324,22 @@ __global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double*
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) chol[idx] = A[idx];
+    // inverse of E^T W E (what upstream's np.linalg.inv computes): column c of the inverse solves L L^T x = e_c
+    if ((int)threadIdx.x < nA) {
+        const int c = threadIdx.x;
+        double* x = A + nA * nA + c * nA;   // scratch column in shared memory
+        for (int r = 0; r < nA; ++r) {
+            double v = (r == c) ? 1.0 : 0.0;
+            for (int k = 0; k < r; ++k) v -= A[r * nA + k] * x[k];
+            x[r] = v / A[r * nA + r];
+        }
+        for (int r = nA - 1; r >= 0; --r) {
+            double v = x[r];
+            for (int k = r + 1; k < nA; ++k) v -= A[k * nA + r] * x[k];
+            x[r] = v / A[r * nA + r];
+        }
+        for (int r = 0; r < nA; ++r) ainv[r * nA + c] = x[r];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -18,7 +18,20 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "dks_kernels.cuh"
+
+// tuning switches (compile-time; the defaults are the measured best)
+#ifndef DKS_TC_WARP_POLL
+#define DKS_TC_WARP_POLL 0      // 1: only lane 0 of a warp polls an mbarrier
+#endif
+#ifndef DKS_TC_WARP_ARRIVE
+#define DKS_TC_WARP_ARRIVE 0    // 1: one mbarrier arrival per warp instead of per thread
+#endif
+#ifndef DKS_TC_PREFETCH
+#define DKS_TC_PREFETCH 0       // 1: double-buffered tcgen05.ld and early accumulator release
+#endif
 
 namespace dks {
 namespace tc {
@@ -66,6 +79,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* s
         }
     }
 }
+// one polling lane per warp (fewer SYNCS operations on the barrier); __syncwarp orders the other lanes behind it
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int* status) {
+#if DKS_TC_WARP_POLL
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, status);
+    __syncwarp();
+#else
+    mbar_wait(bar, parity, status);
+#endif
+}
+// arrival of a whole warp: either every thread arrives, or lane 0 on behalf of the (synchronised) warp
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+#if DKS_TC_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
+constexpr uint32_t ARRIVALS_PER_WARP = DKS_TC_WARP_ARRIVE ? 1u : 32u;
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -141,7 +173,7 @@ struct Smem {
     double* chol;        // [15*15]
     double* rhs;         // [16]
     double* part;        // [N_WLS_WARPS][16] per-warp partial right-hand sides
-    float2* accs;        // [2][S_cap] (sum p1, sum p0) per coalition row, per instance parity
+    double* ys;          // [2][S_cap] link(ey) - link(fnull) per coalition row, per instance parity
     float* wb;           // [MAX_NPAD] background weights
     uint4* lut;          // [256] byte -> eight bf16 (1.0 / 0.0)
     unsigned char* A;    // [NBUF][128*KP*2]
@@ -149,7 +181,7 @@ struct Smem {
 };
 __host__ __device__ inline size_t smem_bytes(int S_cap, int Npad) {
     return 128 /*bars + tmem ptr*/ + 16 * sizeof(int) + (15 * 15 + 16 + N_WLS_WARPS * 16) * sizeof(double) +
-           2 * (size_t)S_cap * sizeof(float2) + MAX_NPAD * sizeof(float) + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
+           2 * (size_t)S_cap * sizeof(double) + MAX_NPAD * sizeof(float) + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
            2 * NSPLIT * (size_t)Npad * KP * 2 + 64;
 }
 __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
@@ -160,8 +192,8 @@ __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
     s.chol = reinterpret_cast<double*>(base + 128 + 16 * sizeof(int));
     s.rhs = s.chol + 15 * 15;
     s.part = s.rhs + 16;
-    s.accs = reinterpret_cast<float2*>(s.part + N_WLS_WARPS * 16);
-    s.wb = reinterpret_cast<float*>(s.accs + 2 * (size_t)S_cap);
+    s.ys = s.part + N_WLS_WARPS * 16;
+    s.wb = reinterpret_cast<float*>(s.ys + 2 * (size_t)S_cap);
     unsigned char* p = reinterpret_cast<unsigned char*>(s.wb + MAX_NPAD);
     p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     s.lut = reinterpret_cast<uint4*>(p);
@@ -178,6 +210,7 @@ struct TcParams {
     int uniform_w;
     float* dbg_T;          // optional [S_cap][Npad] dump of the scores of instance dbg_i
     int dbg_i;
+    int ablate;            // bring-up aid (env DKS_TC_ABLATE, bit mask): knocks out one pipeline stage for timing
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -258,9 +291,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
     const size_t slab = (size_t)p.n * G;
 
     if (threadIdx.x == 0) {
-        for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
-        mbar_init(&inst_full[0], 32 * N_EPI_WARPS); mbar_init(&inst_full[1], 32 * N_EPI_WARPS);
-        mbar_init(&inst_empty[0], 32 * N_WLS_WARPS); mbar_init(&inst_empty[1], 32 * N_WLS_WARPS);
+        // arrivals are per warp (lane 0 after __syncwarp), not per thread
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4 * ARRIVALS_PER_WARP); }
+        mbar_init(&inst_full[0], N_EPI_WARPS * ARRIVALS_PER_WARP); mbar_init(&inst_full[1], N_EPI_WARPS * ARRIVALS_PER_WARP);
+        mbar_init(&inst_empty[0], N_WLS_WARPS * ARRIVALS_PER_WARP); mbar_init(&inst_empty[1], N_WLS_WARPS * ARRIVALS_PER_WARP);
         fence_barrier_init();
     }
     // weights of the padded columns are zero; with uniform weights the sums stay unnormalised (weight 1)
@@ -300,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             }
             named_bar_sync(2, PROD_THREADS);
             const int j = ptid;
-            if (j < Npad) {
+            if (j < Npad && !(tp.ablate & 32)) {
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
                     float hi[8], mid[8], lo[8];
@@ -353,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : p.plans[M].z;
             if (g >= 1) {  // every MMA issued so far has completed => the A/B buffers it read are free
                 uint32_t u = (g - 1) / NBUF;
-                mbar_wait(&tmem_full[(g - 1) % NBUF], u & 1, p.status);
+                mbar_wait_warp(&tmem_full[(g - 1) % NBUF], u & 1, p.status);
             }
             if (built_for != i) build_B(i, M, qb & 1);      // only the first instance; later ones are prefetched below
             unsigned char* Bq = sm.B + (size_t)(qb & 1) * NSPLIT * b_split_bytes;
@@ -362,19 +396,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 const int s = t * TILE_S + ptid;
                 uint32_t zz = 0;
                 if (s < S) zz = (uint32_t)(zp[s] & 0xFFFFull) | (1u << M);       // constant column carries score_j
-                if (g >= NBUF) mbar_wait(&tmem_full[buf], (u - 1) & 1, p.status);     // A[buf] free (MMA g-NBUF done)
+                if (g >= NBUF) mbar_wait_warp(&tmem_full[buf], (u - 1) & 1, p.status); // A[buf] free (MMA g-NBUF done)
                 unsigned char* Ab = sm.A + (size_t)buf * a_bytes;
-                *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + ptid * 16) = sm.lut[zz & 0xFFu];
-                *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + ptid * 16) = sm.lut[(zz >> 8) & 0xFFu];
-                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-                named_bar_sync(2, PROD_THREADS);
+                if (!(tp.ablate & 16) || g < NBUF) {
+                    *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + ptid * 16) = sm.lut[zz & 0xFFu];
+                    *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + ptid * 16) = sm.lut[(zz >> 8) & 0xFFu];
+                    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+                    named_bar_sync(2, PROD_THREADS);
+                }
                 if (ptid == 0) {
                     mbar_wait(&tmem_empty[buf], (u & 1) ^ 1, p.status);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(Ab), TILE_S * 16, 128);
                     const uint32_t d_tmem = tmem_base + buf * 128;
 #pragma unroll
-                    for (int sp = 0; sp < NSPLIT; ++sp) {
+                    for (int sp = 0; sp < ((tp.ablate & 2) ? 1 : NSPLIT); ++sp) {
                         const uint64_t bdesc = make_smem_desc(smem_u32(Bq + sp * b_split_bytes), (uint32_t)Npad * 16, 128);
                         umma_bf16(d_tmem, adesc, bdesc, idesc, sp > 0 ? 1u : 0u);
                     }
@@ -387,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                     int Mn;
                     int inext = next_work(i, Mn);
                     if (inext >= 0) {
-                        mbar_wait(&tmem_full[buf], u & 1, p.status);
+                        mbar_wait_warp(&tmem_full[buf], u & 1, p.status);
                         build_B(inext, Mn, (qb + 1) & 1);
                         built_for = inext;
                     }
@@ -407,42 +443,99 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         const int ntail = N - nfull * 16;             // background rows in the last, partial chunk
         const int nchunks = nfull + (ntail ? 1 : 0);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 128;
+        const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
+        const float inv_n = 1.0f / (float)N;
 
         uint32_t g = 0;
         int q = 0;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
             int M, S;
             const int T = tiles_of(p, i, M, S);
-            float2* accs = sm.accs + (size_t)(q & 1) * p.S_cap;
+            double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
             bool waited = false;
             for (int t = 0; t < T; ++t, ++g) {
                 if ((int)(g % NBUF) != grp) continue;
                 const uint32_t u = g / NBUF;
                 const int s = t * TILE_S + row_in_tile;
-                mbar_wait(&tmem_full[grp], u & 1, p.status);
+                mbar_wait_warp(&tmem_full[grp], u & 1, p.status);
                 tc_fence_after();
                 float acc1 = 0.f, acc0 = 0.f;
+#if DKS_TC_PREFETCH
+                float va[16], vb[16];
+                auto release = [&]() {               // every chunk of this tile is in registers: free the accumulator
+                    tc_fence_before();
+                    mbar_arrive_warp(&tmem_empty[grp]);
+                };
+                if (tp.ablate & 8) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) { va[jj] = 0.01f * jj; vb[jj] = 0.02f * jj; }
+                } else {
+                    tmem_ld16(taddr, va);
+                    tmem_ld_wait(va);
+                }
+                if (nchunks == 1) release();
+                for (int c = 0; c < nchunks; c += 2) {
+                    const bool has_b = c + 1 < nchunks, has_next = c + 2 < nchunks;
+                    if (has_b && !(tp.ablate & 8)) tmem_ld16(taddr + (c + 1) * 16, vb);  // in flight during consume(va)
+                    if (DBG) {
+                        if (i == tp.dbg_i && s < p.S_cap)
+                            for (int jj = 0; jj < 16; ++jj) tp.dbg_T[(size_t)s * Npad + c * 16 + jj] = va[jj];
+                    }
+                    if (tp.ablate & 1) { acc1 += va[0]; acc0 += 1.f; }
+                    else if (c < nfull) consume16<UW>(va, sm.wb + c * 16, acc1, acc0);
+                    else consume_tail(va, sm.wb + c * 16, ntail, acc1, acc0);
+                    if (has_b) {
+                        if (!(tp.ablate & 8)) tmem_ld_wait(vb);
+                        if (!has_next) release();
+                        if (has_next && !(tp.ablate & 8)) tmem_ld16(taddr + (c + 2) * 16, va);
+                        if (DBG) {
+                            if (i == tp.dbg_i && s < p.S_cap)
+                                for (int jj = 0; jj < 16; ++jj) tp.dbg_T[(size_t)s * Npad + (c + 1) * 16 + jj] = vb[jj];
+                        }
+                        if (tp.ablate & 1) { acc1 += vb[0]; acc0 += 1.f; }
+                        else if (c + 1 < nfull) consume16<UW>(vb, sm.wb + (c + 1) * 16, acc1, acc0);
+                        else consume_tail(vb, sm.wb + (c + 1) * 16, ntail, acc1, acc0);
+                        if (has_next) {
+                            if (!(tp.ablate & 8)) tmem_ld_wait(va);
+                            if (c + 3 >= nchunks) release();     // va holds the last chunk
+                        }
+                    }
+                }
+#else
                 for (int c = 0; c < nchunks; ++c) {
                     float v[16];
-                    tmem_ld16(taddr + c * 16, v);
-                    tmem_ld_wait(v);
+                    if (tp.ablate & 8) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = 0.01f * (float)(jj + c);
+                    } else {
+                        tmem_ld16(taddr + c * 16, v);
+                        tmem_ld_wait(v);
+                    }
                     if (DBG) {
                         if (i == tp.dbg_i && s < p.S_cap)
                             for (int jj = 0; jj < 16; ++jj) tp.dbg_T[(size_t)s * Npad + c * 16 + jj] = v[jj];
                     }
-                    if (c < nfull) consume16<UW>(v, sm.wb + c * 16, acc1, acc0);
+                    if (tp.ablate & 1) { acc1 += v[0]; acc0 += 1.f; }
+                    else if (c < nfull) consume16<UW>(v, sm.wb + c * 16, acc1, acc0);
                     else consume_tail(v, sm.wb + c * 16, ntail, acc1, acc0);
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[grp]);       // accumulator buffer may be overwritten
+                mbar_arrive_warp(&tmem_empty[grp]);  // accumulator buffer may be overwritten
+#endif
                 if (!waited) {   // the row buffer of ordinal q-2 must have been consumed by the WLS warps
-                    mbar_wait(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
+                    mbar_wait_warp(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
                     waited = true;
                 }
-                if (s < S) accs[s] = make_float2(acc1, acc0);
+                if (s < S && !(tp.ablate & 512)) {
+                    // link(ey) - link(fnull); with the logit link the normalisation of the sums cancels
+                    double y;
+                    if (p.link == DKS_LINK_LOGIT) y = log((double)acc1 / (double)acc0) - lf1;
+                    else y = (double)(UW ? acc1 * inv_n : acc1) - f1;
+                    ys[s] = y;
+                }
             }
-            if (!waited) mbar_wait(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
-            mbar_arrive(&inst_full[q & 1]);          // release-arrive: publishes this thread's rows
+            if (!waited) mbar_wait_warp(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
+            mbar_arrive_warp(&inst_full[q & 1]);     // release-arrive: publishes the rows written by this warp
         }
     } else {
         // =================================== WLS warpgroup (float64) ===================================
@@ -451,18 +544,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         const int ww = warp - (N_PROD_WARPS + N_EPI_WARPS);                  // 0..3
         const int wtid = threadIdx.x - 32 * (N_PROD_WARPS + N_EPI_WARPS);     // 0..127
         constexpr int WLS_THREADS = 32 * N_WLS_WARPS;
-        const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
-        const double inv_n = 1.0 / (double)N;
         int cachedM = -1;
+        bool have_inverse = false;
         int q = 0;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
             int M, S;
             const int T = tiles_of(p, i, M, S);
             const int C = p.C;
-            for (int idx = wtid; idx < C * G; idx += WLS_THREADS)
-                p.phi[(size_t)(idx / G) * slab + (size_t)i * G + idx % G] = 0.0;
+            if (!(tp.ablate & 256))
+                for (int idx = wtid; idx < C * G; idx += WLS_THREADS)
+                    p.phi[(size_t)(idx / G) * slab + (size_t)i * G + idx % G] = 0.0;
             if (T == 0) {
-                mbar_wait(&inst_full[q & 1], (q >> 1) & 1, p.status);
+                mbar_wait_warp(&inst_full[q & 1], (q >> 1) & 1, p.status);
                 if (M == 1) {
                     if (wtid < C) {
                         int gI = __ffsll((long long)p.vmask[i]) - 1;
@@ -474,7 +567,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                     if (missing) { atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING); p.status[1] = M; }
                     else { atomicCAS(&p.status[0], 0, DKS_ERR_INVALID); p.status[1] = i; }
                 }
-                mbar_arrive(&inst_empty[q & 1]);
+                mbar_arrive_warp(&inst_empty[q & 1]);
                 continue;
             }
             const int nA = M - 1, L = M - 1;
@@ -484,14 +577,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             // factored here, overlapping the epilogue of the same instance
             if (p.ext_z == nullptr) {
                 zp = p.plans[M].z; wp = p.plans[M].w;
-                const double* chol = p.plans[M].chol;
+                const double* ainv = p.plans[M].ainv;        // inverse of E^T W E, computed once per plan
                 if (M != cachedM) {
                     named_bar_sync(1, WLS_THREADS);
-                    for (int idx = wtid; idx < nA * nA; idx += WLS_THREADS) sm.chol[idx] = chol[idx];
+                    for (int idx = wtid; idx < nA * nA; idx += WLS_THREADS) sm.chol[idx] = ainv[idx];
                     cachedM = M;
                 }
+                have_inverse = true;
             } else {
                 cachedM = -1;
+                have_inverse = false;
                 zp = p.ext_z + (size_t)i * p.ext_stride;
                 wp = p.ext_w + (size_t)i * p.ext_stride;
                 named_bar_sync(1, WLS_THREADS);
@@ -503,18 +598,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 }
             }
             const double delta = p.dlink[(size_t)i * C + 1];
-            mbar_wait(&inst_full[q & 1], (q >> 1) & 1, p.status);
-            const float2* accs = sm.accs + (size_t)(q & 1) * p.S_cap;
+            mbar_wait_warp(&inst_full[q & 1], (q >> 1) & 1, p.status);
+            const double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
             double Tk[KP - 1];
 #pragma unroll
             for (int k = 0; k < KP - 1; ++k) Tk[k] = 0.0;
-            for (int s = wtid; s < S; s += WLS_THREADS) {
-                const float2 a = accs[s];
+            for (int s = wtid; s < ((tp.ablate & 4) ? 0 : S); s += WLS_THREADS) {
+                const double y = ys[s];
                 const uint64_t zrow = zp[s];
                 const double wrow = wp[s];
-                double y;
-                if (p.link == DKS_LINK_LOGIT) y = log((double)a.x / (double)a.y) - lf1;
-                else y = (UW ? (double)a.x * inv_n : (double)a.x) - f1;
                 // fold the row into E^T W y:  e_k = z_k - z_L = (z_L ? -1 : 1) * z'_k with z' = z_L ? ~z : z
                 const bool zl = (zrow >> L) & 1ull;
                 double v = wrow * (y - (zl ? delta : 0.0));
@@ -526,17 +618,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             }
 #pragma unroll
             for (int k = 0; k < KP - 1; ++k)
-                if (k < nA) {
+                if (k < nA && !(tp.ablate & 128)) {
                     double r = warp_sum(Tk[k]);
                     if (lane == 0) sm.part[ww * 16 + k] = r;
                 }
             named_bar_sync(1, WLS_THREADS);
-            if (wtid == 0) {
-                for (int k = 0; k < nA; ++k) {           // fixed summation order: deterministic results
-                    double acc = 0.0;
-                    for (int e = 0; e < N_WLS_WARPS; ++e) acc += sm.part[e * 16 + k];
-                    sm.rhs[k] = acc;
+            if (wtid < nA) {                              // fixed summation order: deterministic results
+                double acc = 0.0;
+                for (int e = 0; e < N_WLS_WARPS; ++e) acc += sm.part[e * 16 + wtid];
+                sm.rhs[wtid] = acc;
+            }
+            named_bar_sync(1, WLS_THREADS);
+            if (have_inverse) {
+                // beta = inv(E^T W E) (E^T W y): one thread per coefficient, then phi (both classes) by warp 0
+                double beta = 0.0;
+                if (ww == 0 && lane < nA && !(tp.ablate & 64)) {
+                    for (int l = 0; l < nA; ++l) beta = fma(sm.chol[lane * nA + l], sm.rhs[l], beta);
                 }
+                if (ww == 0) {
+                    double sum = beta;                    // lanes >= nA hold 0
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    // lane k < nA owns varying position k, lane nA the eliminated (last) one
+                    double val = lane < nA ? beta : delta - sum;
+                    if (fabs(val) < 1e-10) val = 0.0;
+                    if (lane < M) {
+                        const uint64_t vm = p.vmask[i];
+                        int cnt = 0, gsel = 0;
+                        for (int gI = 0; gI < G; ++gI)
+                            if ((vm >> gI) & 1ull) { if (cnt == lane) gsel = gI; ++cnt; }
+                        p.phi[slab + (size_t)i * G + gsel] = val;
+                        p.phi[(size_t)i * G + gsel] = (val == 0.0) ? 0.0 : -val;
+                    }
+                }
+            } else if (wtid == 0) {
                 int vi[KP];
                 {
                     const uint64_t vm = p.vmask[i];
@@ -549,7 +664,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 for (int k = 0; k < M; ++k) { double v = phi1[vi[k]]; phi0[vi[k]] = (v == 0.0) ? 0.0 : -v; }
             }
             named_bar_sync(1, WLS_THREADS);
-            mbar_arrive(&inst_empty[q & 1]);
+            mbar_arrive_warp(&inst_empty[q & 1]);
         }
     }
 
@@ -580,6 +695,8 @@ inline int tc_launch(dks_ctx* ctx, const ExplainParams& p) {
     tp.uniform_w = ctx->uniform_w ? 1 : 0;
     tp.dbg_T = ctx->dbg_T;
     tp.dbg_i = ctx->dbg_i;
+    const char* ab = getenv("DKS_TC_ABLATE");
+    tp.ablate = ab ? atoi(ab) : 0;
     size_t smem = tc::smem_bytes(p.S_cap, tp.Npad);
     void (*kern)(tc::TcParams) = nullptr;
     const bool dbg = tp.dbg_T != nullptr && tp.dbg_i >= 0;
