@@ -30,6 +30,7 @@ LINK_LOGIT = 1
 KERNEL_AUTO = 0
 KERNEL_SIMT = 1
 KERNEL_TCGEN05 = 2
+KERNEL_SHARED = 3
 
 # name -> (restype, argtypes); every symbol include/dks.h declares
 SIGNATURES = {
@@ -64,6 +65,7 @@ SIGNATURES = {
     "dks_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dks_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dks_debug_score_dump": (C.c_int, [C.c_void_p, C.c_int]),
+    "dks_debug_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dks_debug_get_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 

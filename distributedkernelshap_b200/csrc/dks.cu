@@ -6,6 +6,7 @@
 
 #include "dks_kernels.cuh"
 #include "dks_tc.cuh"
+#include "dks_shared.cuh"
 
 namespace {
 
@@ -74,6 +75,8 @@ int ensure_workspace(dks_ctx* ctx, int n) {
     TRY(dev_alloc(&ctx->d_vmask, (size_t)n));
     TRY(dev_alloc(&ctx->d_M, (size_t)n));
     TRY(dev_alloc(&ctx->d_dlink, (size_t)n * C));
+    TRY(dev_alloc(&ctx->d_idx_full, (size_t)n));
+    TRY(dev_alloc(&ctx->d_idx_other, (size_t)n));
     ctx->cap_n = n;
     return DKS_OK;
 }
@@ -81,16 +84,17 @@ int ensure_workspace(dks_ctx* ctx, int n) {
 int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
     const int G = ctx->G;
     TRY(ensure_workspace(ctx, n));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
+    // histogram, status word and list counters are adjacent: one memset
+    CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4), ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    dks::prep_group_kernel<<<cdiv((long long)n * G, 256), 256, 0, ctx->stream>>>(
-        X_dev, ctx->d_W, ctx->d_bg, ctx->d_goff, ctx->d_gcols, ctx->d_colmin, ctx->d_colmax, ctx->d_colnan, n, ctx->N,
-        ctx->D, G, ctx->R, ctx->d_XW, ctx->d_vflag);
-    dks::prep_instance_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(
-        ctx->d_XW, ctx->d_vflag, ctx->d_b, ctx->d_linkfnull, n, G, ctx->R, ctx->C, ctx->act, ctx->kappa, ctx->link,
-        ctx->d_vmask, ctx->d_M, ctx->d_dlink, ctx->d_hist);
-    ctx->launches += 2;
+    int ipb = 256 / G;
+    if (ipb < 1) ipb = 1;
+    size_t psm = sizeof(double) * (size_t)ipb * G * ctx->R + (size_t)ipb * G;
+    dks::prep_kernel<<<cdiv(n, ipb), 256, psm, ctx->stream>>>(
+        X_dev, ctx->d_W, ctx->d_b, ctx->d_bg, ctx->d_goff, ctx->d_gcols, ctx->d_colmin, ctx->d_colmax, ctx->d_colnan,
+        ctx->d_linkfnull, n, ctx->N, ctx->D, G, ctx->R, ctx->C, ctx->act, ctx->kappa, ctx->link, ipb, ctx->d_XW,
+        ctx->d_vmask, ctx->d_M, ctx->d_dlink, ctx->d_hist, ctx->d_counts, ctx->d_idx_full, ctx->d_idx_other);
+    ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->cur_n = n;
@@ -127,11 +131,44 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             ctx->dbg_rows = rows; ctx->dbg_cols = cols;
         }
         CUDA_TRY(cudaMemsetAsync(ctx->dbg_T, 0, sizeof(float) * rows * cols, ctx->stream));
+        if (!ctx->dbg_time) TRY(dev_alloc(&ctx->dbg_time, (size_t)6 * 256));
+        CUDA_TRY(cudaMemsetAsync(ctx->dbg_time, 0, sizeof(float) * 6 * 256, ctx->stream));
     }
 
     int kernel = ctx->kernel_choice;
-    if (kernel == DKS_KERNEL_AUTO) kernel = dks::tc_supported(ctx, p) ? DKS_KERNEL_TCGEN05 : DKS_KERNEL_SIMT;
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    // ---- shared-plan fast path: instances whose varying set is all G groups, evaluated against the plan's Dm table
+    const int G = ctx->G;
+    const PlanDev& pg = ctx->h_plans[G <= DKS_MAX_GROUPS ? G : 0];
+    const bool fast = (kernel == DKS_KERNEL_AUTO || kernel == DKS_KERNEL_SHARED) && ext_z == nullptr &&
+                      ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->uniform_w && G >= 2 && pg.dmT != nullptr &&
+                      pg.S == dks_effective_S(G, ctx->nsamples_req);
+    if (kernel == DKS_KERNEL_SHARED && !fast && ext_z == nullptr && pg.z != nullptr)
+        return fail(DKS_ERR_UNSUPPORTED, "shared-plan fast path needs the binary-logistic head, uniform background weights "
+                    "and at most %d background rows", dks::shared_path::MAXN);
+    if (fast) {
+        const int S = pg.S, S_pad = pg.S_pad;
+        size_t need = (size_t)n * S_pad;
+        if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; }
+        dks::shared_path::SharedParams sp;
+        sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
+        sp.DmT = pg.dmT; sp.z = pg.z; sp.XW = ctx->d_XW; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums;
+        dks::shared_path::launch_explain_shared(sp, ctx->sm_count, ctx->stream);
+        dks::shared_path::WlsSharedParams wp;
+        wp.n = n; wp.N = ctx->N; wp.G = G; wp.C = ctx->C; wp.S = S; wp.S_pad = S_pad; wp.link = ctx->link;
+        wp.uniform_w = 1; wp.sums = ctx->d_sums; wp.z = pg.z; wp.w = pg.w; wp.ainv = pg.ainv; wp.dlink = ctx->d_dlink;
+        wp.linkfnull = ctx->d_linkfnull; wp.fnull = ctx->d_fnull; wp.list = ctx->d_idx_full; wp.count = ctx->d_counts;
+        wp.phi = phi_dev;
+        int wgrid = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;     // persistent: ~4 CTAs of 8 warps per SM
+        dks::shared_path::wls_shared_kernel<<<wgrid, dks::shared_path::WLS_THREADS, 0, ctx->stream>>>(wp);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        p.list = ctx->d_idx_other;      // the general kernel below takes the remaining instances
+        p.count = ctx->d_counts + 1;
+    }
+    if (kernel == DKS_KERNEL_AUTO || kernel == DKS_KERNEL_SHARED)
+        kernel = dks::tc_supported(ctx, p) ? DKS_KERNEL_TCGEN05 : DKS_KERNEL_SIMT;
     if (kernel == DKS_KERNEL_TCGEN05) {
         if (!dks::tc_supported(ctx, p))
             return fail(DKS_ERR_UNSUPPORTED, "tcgen05 kernel does not support this shape/head (N=%d G=%d act=%d)", ctx->N,
@@ -206,9 +243,10 @@ int dks_create(dks_ctx** out, int device) {
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaMalloc((void**)&ctx->d_plans, sizeof(ctx->h_plans)));
     CUDA_TRY(cudaMemset(ctx->d_plans, 0, sizeof(ctx->h_plans)));
-    CUDA_TRY(cudaMalloc((void**)&ctx->d_hist, sizeof(int) * (DKS_MAX_GROUPS + 1)));
-    CUDA_TRY(cudaMalloc((void**)&ctx->d_status, sizeof(int) * 2));
-    CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int) * 2));
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_hist, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4)));   // histogram, status, list counts
+    ctx->d_status = ctx->d_hist + (DKS_MAX_GROUPS + 1);
+    ctx->d_counts = ctx->d_status + 2;
+    CUDA_TRY(cudaMemset(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4)));
     *out = ctx;
     return DKS_OK;
 }
@@ -223,9 +261,11 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
-    dev_free(&ctx->d_hist); dev_free(&ctx->d_status); dev_free(&ctx->d_phi); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums);
+    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
+    dev_free(&ctx->dbg_time);
     for (void* p : ctx->plan_allocs) cudaFree(p);
     dks::tc_release(ctx);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -379,6 +419,13 @@ int dks_fit(dks_ctx* ctx) {
     CUDA_TRY(cudaStreamSynchronize(st));
     ctx->cap_n = 0;  // workspace shapes depend on G, R, C
     ctx->prepared = false;
+    if (!ctx->plan_allocs.empty()) {   // plans carry tables derived from the background/model: drop them
+        for (void* q : ctx->plan_allocs) cudaFree(q);
+        ctx->plan_allocs.clear();
+        memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+        ctx->max_plan_S = 0;
+        CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
+    }
     TRY(dks::tc_fit(ctx));
     ctx->fitted = true;
     return DKS_OK;
@@ -457,6 +504,19 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     PlanDev pd;
     memset(&pd, 0, sizeof(pd));
     pd.z = dz; pd.w = dw; pd.chol = dc; pd.ainv = di; pd.S = S;
+    pd.S_pad = (S + 31) / 32 * 32;
+    if (M == ctx->G && ctx->fitted && ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->N <= dks::shared_path::MAXN) {
+        // shared-plan fast path: Dm table for the full varying set
+        float* dm = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&dm, sizeof(float) * (size_t)ctx->N * pd.S_pad));
+        ctx->plan_allocs.push_back(dm);
+        long long total = (long long)ctx->N * pd.S_pad;
+        dks::shared_path::plan_dm_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(dz, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
+                                                                                      ctx->N, ctx->G, ctx->scale, dm);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        pd.dmT = dm;
+    }
     ctx->h_plans[M] = pd;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -559,7 +619,7 @@ int dks_last_status(dks_ctx* ctx, int* detail) {
 }
 
 int dks_set_kernel(dks_ctx* ctx, int kernel) {
-    REQUIRE(ctx && kernel >= DKS_KERNEL_AUTO && kernel <= DKS_KERNEL_TCGEN05, "dks_set_kernel: unknown kernel %d", kernel);
+    REQUIRE(ctx && kernel >= DKS_KERNEL_AUTO && kernel <= DKS_KERNEL_SHARED, "dks_set_kernel: unknown kernel %d", kernel);
     ctx->kernel_choice = kernel;
     return DKS_OK;
 }
@@ -593,6 +653,14 @@ int dks_debug_get_scores(dks_ctx* ctx, float* out_host, int max_floats, int* row
     REQUIRE((long long)ctx->dbg_rows * ctx->dbg_cols <= max_floats, "dks_debug_get_scores: buffer too small");
     CUDA_TRY(cudaMemcpyAsync(out_host, ctx->dbg_T, sizeof(float) * ctx->dbg_rows * ctx->dbg_cols, cudaMemcpyDeviceToHost,
                              ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DKS_OK;
+}
+
+int dks_debug_get_timeline(dks_ctx* ctx, float* out_host /* [6][256] */) {
+    BIND(ctx);
+    REQUIRE(ctx->dbg_time && out_host, "dks_debug_get_timeline: no timeline available");
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->dbg_time, sizeof(float) * 6 * 256, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DKS_OK;
 }

@@ -17,8 +17,9 @@ struct PlanDev {
     const double* w;     // [S] kernel weights
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
     const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
+    const float* dmT;    // [N][S_pad] 2^(scaled background part of the score) for the full varying set (shared fast path)
     int S;
-    int pad;
+    int S_pad;
 };
 
 // nsamples resolution of KernelExplainer.explain: 'auto' (req <= 0) = 2M + 2^11; capped at 2^M - 2 for M <= 30
@@ -55,7 +56,13 @@ struct ExplainParams {
     int ext_stride;
     double* phi;          // [C][n][G]
     int* status;          // [2] {code, detail}
+    const int* list;      // instances this launch handles (NULL = all n) ...
+    const int* count;     // ... and how many (device memory)
 };
+
+// number of instances a general kernel launch handles and the q-th of them
+__device__ __forceinline__ int dks_inst_count(const ExplainParams& p) { return p.list ? *p.count : p.n; }
+__device__ __forceinline__ int dks_inst_at(const ExplainParams& p, int q) { return p.list ? p.list[q] : q; }
 
 struct dks_ctx {
     int device = 0;
@@ -74,6 +81,7 @@ struct dks_ctx {
     bool uniform_w = true;      // background weights all equal
     float* dbg_T = nullptr;     // debug dump of the tcgen05 score tile of instance dbg_i ([dbg_rows][dbg_cols])
     int dbg_i = -1, dbg_rows = 0, dbg_cols = 0;
+    float* dbg_time = nullptr;  // [6][256] clock64 timeline of CTA 0 (debug kernel variant)
 
     // host copies
     std::vector<double> h_bg, h_wbg, h_W, h_b;
@@ -106,8 +114,13 @@ struct dks_ctx {
     uint64_t* d_vmask = nullptr;
     int* d_M = nullptr;
     double* d_dlink = nullptr;
-    int* d_hist = nullptr;
+    int* d_hist = nullptr;       // [65] histogram of M, then status[2], then list counts[2] (one allocation, one memset)
     int* d_status = nullptr;
+    int* d_counts = nullptr;     // [0] instances on the shared fast path, [1] the others
+    int* d_idx_full = nullptr;   // [n] instances whose varying set is all G groups
+    int* d_idx_other = nullptr;  // [n] the rest
+    float2* d_sums = nullptr;    // [n][S_pad] (sum p1, sum p0) of the shared fast path
+    size_t cap_sums = 0;
     double* d_phi = nullptr;
     size_t cap_phi = 0;
     uint64_t* d_extz = nullptr;

@@ -30,6 +30,47 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- cheap link arithmetic.  Vector FP64 runs at ~16 lanes/clk/SM on this part (as scarce as MUFU), so the per-row
+// work avoids it: the log is evaluated in fp32 around a 64-entry table, and E^T W y is accumulated in fixed point.
+//
+// ln(a1) - ln(a0) for positive float32 sums.  a = 2^e * m, m in [1,2) = c_k (1 + r) with c_k = 1 + (k + 1/2)/64 the centre
+// of the k-th of 64 mantissa intervals, |r| <= 2^-7.  r = m/c_k - 1 is formed with a two-float reciprocal
+// (fmaf(m, rc_hi, -1) + m*rc_lo: abs error ~5e-10) and ln(1+r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5 in fp32 (abs error
+// ~1e-9); only e*ln2 + ln c_k (table, float64) is combined in float64.  Total abs error ~2e-9.
+#define DKS_LOGTAB_SIZE 64
+struct LogTabEntry { float rc_hi, rc_lo; double lnc; };
+__device__ __forceinline__ void logtab_fill(LogTabEntry* tab, int k) {
+    const double c = 1.0 + ((double)k + 0.5) / 64.0;
+    const double rc = 1.0 / c;
+    LogTabEntry e;
+    e.rc_hi = (float)rc;
+    e.rc_lo = (float)(rc - (double)e.rc_hi);
+    e.lnc = log(c);
+    tab[k] = e;
+}
+__device__ __forceinline__ double fast_log_ratio(float a1, float a0, const LogTabEntry* __restrict__ tab) {
+    const int b1 = __float_as_int(a1), b0 = __float_as_int(a0);
+    const LogTabEntry t1 = tab[(b1 >> 17) & 63], t0 = tab[(b0 >> 17) & 63];
+    const float m1 = __int_as_float((b1 & 0x007FFFFF) | 0x3F800000), m0 = __int_as_float((b0 & 0x007FFFFF) | 0x3F800000);
+    const float r1 = fmaf(m1, t1.rc_hi, -1.f) + m1 * t1.rc_lo, r0 = fmaf(m0, t0.rc_hi, -1.f) + m0 * t0.rc_lo;
+    const float p1 = r1 * (1.f + r1 * (-0.5f + r1 * (0.33333334f + r1 * (-0.25f + r1 * 0.2f))));
+    const float p0 = r0 * (1.f + r0 * (-0.5f + r0 * (0.33333334f + r0 * (-0.25f + r0 * 0.2f))));
+    const int de = (b1 >> 23) - (b0 >> 23);
+    return fma((double)de, 0.6931471805599453094, t1.lnc - t0.lnc) + (double)(p1 - p0);
+}
+
+// fixed-point accumulation of E^T W y: v -> round(v * 2^40) as int64 (|v| = w |y| < 8e6 fits), integer adds are exact and
+// order-independent (bit-reproducible whatever the reduction order); resolution 2^-40 ~ 9e-13 per row.
+#define DKS_FIX_SCALE 1099511627776.0          /* 2^40 */
+#define DKS_FIX_INV 9.094947017729282379150390625e-13   /* 2^-40 */
+__device__ __forceinline__ long long to_fix(double v) { return __double2ll_rn(v * DKS_FIX_SCALE); }
+__device__ __forceinline__ double from_fix(long long t) { return (double)t * DKS_FIX_INV; }
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // np.isclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=True) as used by KernelExplainer.not_equal
 __device__ __forceinline__ bool np_isclose(double a, double b) {
     if (a == b) return true;
@@ -163,56 +204,67 @@ __global__ void predict_kernel(const double* __restrict__ X, const double* __res
 // ------------------------------------------------------------------------------------------------------
 // Preparation: grouped instance contributions, varying_groups(), f(x), link deltas
 // ------------------------------------------------------------------------------------------------------
-// one thread per (instance, group): XW[i][g][r] and the "group varies" flag (KernelExplainer.varying_groups)
-__global__ void prep_group_kernel(const double* __restrict__ X, const double* __restrict__ W,
-                                  const double* __restrict__ bg, const int32_t* __restrict__ goff,
-                                  const int32_t* __restrict__ gcols, const double* __restrict__ colmin,
-                                  const double* __restrict__ colmax, const int* __restrict__ colnan, int n, int N,
-                                  int D, int G, int R, double* __restrict__ XW, unsigned char* __restrict__ vflag) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * G) return;
-    int g = idx % G, i = idx / G;
-    bool varies = false;
-    double acc[8];
-    for (int r = 0; r < R && r < 8; ++r) acc[r] = 0;
-    for (int c = goff[g]; c < goff[g + 1]; ++c) {
-        int col = gcols[c];
-        double xv = X[(size_t)i * D + col];
-        for (int r = 0; r < R && r < 8; ++r) acc[r] += xv * W[(size_t)r * D + col];
-        if (!varies) {
-            if (colnan[col] || isnan(xv)) {
-                for (int j = 0; j < N && !varies; ++j) varies = !np_isclose(xv, bg[(size_t)j * D + col]);
-            } else {
-                // |x-b| - rtol|b| is decreasing for b <= x and increasing for b >= x: the extremes decide
-                varies = !np_isclose(xv, colmin[col]) || !np_isclose(xv, colmax[col]);
+// Fused preparation: a block handles `ipb` instances.  Phase 1, one thread per (instance, group): grouped
+// contribution XW[i][g][r] and the "group varies" flag (KernelExplainer.varying_groups); phase 2, one thread per
+// instance: varying bit-mask, M, histogram of M, f(x), link(f(x)) - link(fnull).
+__global__ void prep_kernel(const double* __restrict__ X, const double* __restrict__ W, const double* __restrict__ b,
+                            const double* __restrict__ bg, const int32_t* __restrict__ goff,
+                            const int32_t* __restrict__ gcols, const double* __restrict__ colmin,
+                            const double* __restrict__ colmax, const int* __restrict__ colnan,
+                            const double* __restrict__ linkfnull, int n, int N, int D, int G, int R, int C, int act,
+                            double kappa, int link, int ipb, double* __restrict__ XW, uint64_t* __restrict__ vmask,
+                            int* __restrict__ Mcnt, double* __restrict__ dlink, int* __restrict__ hist,
+                            int* __restrict__ counts, int* __restrict__ idx_full, int* __restrict__ idx_other) {
+    extern __shared__ unsigned char prep_smem[];
+    double* sXW = reinterpret_cast<double*>(prep_smem);                        // [ipb][G][R]
+    unsigned char* sflag = prep_smem + sizeof(double) * (size_t)ipb * G * R;   // [ipb][G]
+    const int i0 = blockIdx.x * ipb;
+    for (int idx = threadIdx.x; idx < ipb * G; idx += blockDim.x) {
+        const int li = idx / G, g = idx - li * G, i = i0 + li;
+        if (i >= n) continue;
+        bool varies = false;
+        double acc[8];
+        for (int r = 0; r < R; ++r) acc[r] = 0;
+        for (int c = goff[g]; c < goff[g + 1]; ++c) {
+            const int col = gcols[c];
+            const double xv = X[(size_t)i * D + col];
+            for (int r = 0; r < R; ++r) acc[r] += xv * W[(size_t)r * D + col];
+            if (!varies) {
+                if (colnan[col] || isnan(xv)) {
+                    for (int j = 0; j < N && !varies; ++j) varies = !np_isclose(xv, bg[(size_t)j * D + col]);
+                } else {
+                    // |x-b| - rtol|b| is decreasing for b <= x and increasing for b >= x: the extremes decide
+                    varies = !np_isclose(xv, colmin[col]) || !np_isclose(xv, colmax[col]);
+                }
             }
         }
+        for (int r = 0; r < R; ++r) {
+            sXW[(size_t)idx * R + r] = acc[r];
+            XW[((size_t)i * G + g) * R + r] = acc[r];
+        }
+        sflag[idx] = varies ? 1 : 0;
     }
-    for (int r = 0; r < R && r < 8; ++r) XW[(size_t)idx * R + r] = acc[r];
-    vflag[idx] = varies ? 1 : 0;
-}
-
-// one thread per instance: varying bit-mask, M, histogram of M, f(x), link(f(x)) - link(fnull)
-__global__ void prep_instance_kernel(const double* __restrict__ XW, const unsigned char* __restrict__ vflag,
-                                     const double* __restrict__ b, const double* __restrict__ linkfnull, int n,
-                                     int G, int R, int C, int act, double kappa, int link,
-                                     uint64_t* __restrict__ vmask, int* __restrict__ Mcnt,
-                                     double* __restrict__ dlink, int* __restrict__ hist) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t m = 0;
-    double z[8], o[DKS_MAX_GROUPS];
-    for (int r = 0; r < R; ++r) z[r] = b[r];
-    for (int g = 0; g < G; ++g) {
-        if (vflag[(size_t)i * G + g]) m |= (1ull << g);
-        for (int r = 0; r < R; ++r) z[r] += XW[((size_t)i * G + g) * R + r];
+    __syncthreads();
+    for (int li = threadIdx.x; li < ipb; li += blockDim.x) {
+        const int i = i0 + li;
+        if (i >= n) continue;
+        uint64_t m = 0;
+        double z[8], o[DKS_MAX_GROUPS];
+        for (int r = 0; r < R; ++r) z[r] = b[r];
+        for (int g = 0; g < G; ++g) {
+            if (sflag[li * G + g]) m |= (1ull << g);
+            for (int r = 0; r < R; ++r) z[r] += sXW[((size_t)li * G + g) * R + r];
+        }
+        const int M = __popcll(m);
+        vmask[i] = m;
+        Mcnt[i] = M;
+        atomicAdd(&hist[M], 1);
+        // bucket: all groups vary (candidates for the shared-plan fast path) / everything else
+        if (M == G && M >= 2) idx_full[atomicAdd(&counts[0], 1)] = i;
+        else idx_other[atomicAdd(&counts[1], 1)] = i;
+        head_f64(z, R, act, kappa, o);
+        for (int c = 0; c < C; ++c) dlink[(size_t)i * C + c] = link_f(o[c], link) - linkfnull[c];
     }
-    int M = __popcll(m);
-    vmask[i] = m;
-    Mcnt[i] = M;
-    atomicAdd(&hist[M], 1);
-    head_f64(z, R, act, kappa, o);
-    for (int c = 0; c < C; ++c) dlink[(size_t)i * C + c] = link_f(o[c], link) - linkfnull[c];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -378,7 +430,9 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
     const int N = p.N, G = p.G, C = p.C;
     const size_t slab = (size_t)p.n * G;
 
-    for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
+    const int ninst = dks_inst_count(p);
+    for (int qi = blockIdx.x; qi < ninst; qi += gridDim.x) {
+        const int i = dks_inst_at(p, qi);
         const int M = p.Mcnt[i];
         const uint64_t vm = p.vmask[i];
         __syncthreads();  // previous instance done with shared memory

@@ -1,0 +1,274 @@
+// Shared-plan fast path of the fused coalition evaluation (binary-logistic head).
+//
+// When every instance of a bucket evaluates the SAME coalition plan and all G groups vary (the common case: on
+// Adult-shaped data every instance has M = G), the masked score separates:
+//     t(i, s, j) = a(i, s) + d(s, j),   a(i, s) = scale * sum_k z_sk XW_i[k],   d(s, j) = scale * (score_j - sum_k z_sk BW[j][k])
+// so  2^t = A(i, s) * Dm(s, j)  with Dm = 2^d independent of the instance.  Dm (S x N floats, 0.8 MB for Adult) is
+// computed once per plan; every lane keeps its coalition row of Dm in REGISTERS and streams ~n/27 instances through it:
+// per element one FMUL instead of a GEMM + EX2, and with the paired reciprocal 0.5 MUFU op.  Output: (sum p1, sum p0)
+// per (instance, coalition); wls_shared_kernel applies the link and solves with the plan's precomputed inverse.
+// Instances with a partial varying set, per-instance plans and other heads go through the general kernels.
+#pragma once
+
+#include "dks_kernels.cuh"
+
+namespace dks {
+namespace shared_path {
+
+constexpr int MAXN = 128;            // background rows held in registers per lane
+constexpr int WARPS_PER_CTA = 12;
+constexpr float U_CLAMP = 1.152921504606846976e18f;   // 2^60: (1 + ua)(1 + ub) stays finite in fp32
+
+// DmT[j][s] = 2^(scale * (score_j - sum_k z_sk BW[j][k]))  for the full varying set (k = group index), float32,
+// transposed so that consecutive coalitions are contiguous (coalesced row loads by lanes)
+__global__ void plan_dm_kernel(const uint64_t* __restrict__ z, int S, int S_pad, const double* __restrict__ BW,
+                               const double* __restrict__ scores, int N, int G, double scale, float* __restrict__ DmT) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * S_pad) return;
+    const int j = idx / S_pad, s = idx - j * S_pad;
+    float out = 0.f;
+    if (s < S) {
+        const uint64_t zz = z[s];
+        double c = 0.0;
+        for (int k = 0; k < G; ++k)
+            if ((zz >> k) & 1ull) c += BW[(size_t)j * G + k];
+        out = (float)exp2(scale * (scores[j] - c));
+    }
+    DmT[idx] = out;
+}
+
+struct SharedParams {
+    int n, N, G, S, S_pad;
+    double scale;
+    const float* DmT;        // [N][S_pad]
+    const uint64_t* z;       // [S]
+    const double* XW;        // [n][G]
+    const int* list;         // instances on this path
+    const int* count;        // their number (device)
+    float2* sums;            // [n][S_pad] (sum p1, sum p0)
+};
+
+// Two sigmoids with one reciprocal.  With ua = 2^ta, ub = 2^tb:  (1+ua)(1+ub) = 1 + sm + q,  sm = ua + ub, q = ua*ub
+//   p1a + p1b = (2 + sm) / (1 + sm + q)          p0a + p0b = (sm + 2q) / (1 + sm + q)
+// 12 FP32-pipe ops + 1 MUFU per pair.  CLAMP: bound u at 2^60 so q cannot overflow (only needed for extreme scores).
+template <bool CLAMP>
+__device__ __forceinline__ void pair_acc(float A, float dma, float dmb, float& a1, float& a0) {
+    float ua = A * dma, ub = A * dmb;
+    if (CLAMP) { ua = fminf(ua, U_CLAMP); ub = fminf(ub, U_CLAMP); }
+    const float q = ua * ub, sm = ua + ub;
+    const float t1 = 1.f + sm;
+    const float r = rcp_approx(fmaf(ua, ub, t1));
+    a1 = fmaf(r, t1 + 1.f, a1);
+    a0 = fmaf(r, fmaf(2.f, q, sm), a0);
+}
+__device__ __forceinline__ void single_acc(float A, float dma, float& a1, float& a0) {
+    const float ua = fminf(A * dma, U_CLAMP);
+    const float r = rcp_approx(1.f + ua);
+    a1 += r;
+    a0 = fmaf(ua, r, a0);
+}
+
+// NTAIL = N % 16 (compile time): the last, partial chunk is straight-line code
+template <bool CLAMP, int NTAIL>
+__device__ __forceinline__ void row_sums(const float (&dm)[MAXN], float A, int nfull, float& s1, float& s0) {
+    float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc0[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < MAXN / 16; ++c) {
+        if (c < nfull) {
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2)
+                pair_acc<CLAMP>(A, dm[c * 16 + jj], dm[c * 16 + jj + 1], acc1[(jj >> 1) & 3], acc0[(jj >> 1) & 3]);
+        } else if (NTAIL > 0 && c == nfull) {
+#pragma unroll
+            for (int jj = 0; jj + 1 < NTAIL; jj += 2)
+                pair_acc<CLAMP>(A, dm[c * 16 + jj], dm[c * 16 + jj + 1], acc1[(jj >> 1) & 3], acc0[(jj >> 1) & 3]);
+            if (NTAIL & 1) single_acc(A, dm[c * 16 + NTAIL - 1], acc1[3], acc0[3]);   // odd number of background rows
+        }
+    }
+    s1 = (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]);
+    s0 = (acc0[0] + acc0[1]) + (acc0[2] + acc0[3]);
+}
+
+// one warp = 32 coalition rows (one per lane) x a strided subset of the instances
+template <int NTAIL>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(SharedParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int n_rg = p.S_pad / 32;                       // row groups
+    const int total_warps = gridDim.x * WARPS_PER_CTA;
+    const int nparts = total_warps / n_rg;               // replicas of every row group
+    if (nparts == 0 || gw >= nparts * n_rg) return;
+    const int rg = gw % n_rg, part = gw / n_rg;
+    const int s = rg * 32 + lane;
+    const int cnt = *p.count;
+    const int N = p.N, G = p.G;
+
+    // this lane's row of Dm, in registers (chunks of 16 columns; unused chunks are never touched)
+    float dm[MAXN];
+    float dmax = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXN / 16; ++c) {
+        if (c * 16 < N) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int j = c * 16 + jj;
+                dm[j] = j < N ? p.DmT[(size_t)j * p.S_pad + s] : 0.f;
+                dmax = fmaxf(dmax, dm[j]);
+            }
+        }
+    }
+    const uint64_t zz = s < p.S ? p.z[s] : 0ull;
+    const int nfull = N / 16;
+
+    // lanes k and k+32 hold XW_i[k], XW_i[k+32] of the NEXT instance (coalesced load, one iteration ahead)
+    double xw_lo = 0.0, xw_hi = 0.0;
+    int i_next = part < cnt ? p.list[part] : -1;
+    if (i_next >= 0) {
+        if (lane < G) xw_lo = p.XW[(size_t)i_next * G + lane];
+        if (lane + 32 < G) xw_hi = p.XW[(size_t)i_next * G + lane + 32];
+    }
+    for (int m = part; m < cnt; m += nparts) {
+        const int i = i_next;
+        const double cur_lo = xw_lo, cur_hi = xw_hi;
+        i_next = m + nparts < cnt ? p.list[m + nparts] : -1;
+        if (i_next >= 0) {
+            if (lane < G) xw_lo = p.XW[(size_t)i_next * G + lane];
+            if (lane + 32 < G) xw_hi = p.XW[(size_t)i_next * G + lane + 32];
+        }
+        // a = scale * sum_k z_k XW_i[k] in float64; A = 2^a = 2^n * 2^f with n = rint(a), |f| <= 1/2 (f exact in fp32
+        // to 3e-8, ex2.approx to ~1e-7 relative)
+        double a = 0.0;
+        for (int k = 0; k < G; ++k) {
+            const double xk = __shfl_sync(0xffffffffu, k < 32 ? cur_lo : cur_hi, k & 31);
+            if ((zz >> k) & 1ull) a += xk;
+        }
+        a *= p.scale;
+        a = fmin(fmax(a, -120.0), 120.0);
+        const double an = rint(a);
+        const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
+        float s1, s0;
+        // with u <= 1e18 the product q = ua*ub and the reciprocal of (1+ua)(1+ub) stay normal fp32 numbers: no clamps needed
+        const bool risky = __any_sync(0xffffffffu, A * dmax > 1.0e18f);
+        if (risky) row_sums<true, NTAIL>(dm, A, nfull, s1, s0);
+        else row_sums<false, NTAIL>(dm, A, nfull, s1, s0);
+        if (s < p.S) p.sums[(size_t)i * p.S_pad + s] = make_float2(s1, s0);
+    }
+}
+
+inline void launch_explain_shared(const SharedParams& p, int grid, cudaStream_t stream) {
+    const int threads = 32 * WARPS_PER_CTA;
+    switch (p.N % 16) {
+#define DKS_CASE(T) case T: explain_shared_kernel<T><<<grid, threads, 0, stream>>>(p); break;
+        DKS_CASE(0) DKS_CASE(1) DKS_CASE(2) DKS_CASE(3) DKS_CASE(4) DKS_CASE(5) DKS_CASE(6) DKS_CASE(7)
+        DKS_CASE(8) DKS_CASE(9) DKS_CASE(10) DKS_CASE(11) DKS_CASE(12) DKS_CASE(13) DKS_CASE(14) DKS_CASE(15)
+#undef DKS_CASE
+    }
+}
+
+struct WlsSharedParams {
+    int n, N, G, C, S, S_pad, link, uniform_w;
+    const float2* sums;      // [n][S_pad]
+    const uint64_t* z;
+    const double* w;
+    const double* ainv;      // [(G-1) x (G-1)]
+    const double* dlink;     // [n][C]
+    const double* linkfnull;
+    const double* fnull;
+    const int* list;
+    const int* count;
+    double* phi;             // [C][n][G]
+};
+
+// Persistent CTAs of 8 warps, each looping over instances: y = link(ey) - link(fnull) per coalition, E^T W y in 2^-40
+// fixed point (integer adds: exact, order-independent), beta = inv(E^T W E) (E^T W y), phi.
+constexpr int WLS_THREADS = 256;
+__global__ void __launch_bounds__(WLS_THREADS) wls_shared_kernel(WlsSharedParams p) {
+    __shared__ double s_ainv[63 * 63];
+    __shared__ long long s_part[WLS_THREADS / 32][64];
+    __shared__ double s_rhs[64];
+    __shared__ LogTabEntry s_logtab[DKS_LOGTAB_SIZE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int G = p.G, nA = G - 1, L = G - 1;
+    const int cnt = *p.count;
+    if ((int)blockIdx.x >= cnt) return;
+    if (threadIdx.x < DKS_LOGTAB_SIZE) logtab_fill(s_logtab, threadIdx.x);
+    for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) s_ainv[idx] = p.ainv[idx];
+    __syncthreads();
+    const double lf1 = p.linkfnull[1], f1 = p.fnull[1], inv_n = 1.0 / (double)p.N;
+    const size_t slab = (size_t)p.n * G;
+    for (int m = blockIdx.x; m < cnt; m += gridDim.x) {
+        const int i = p.list[m];
+        const double delta = p.dlink[(size_t)i * p.C + 1];
+        const float2* sums = p.sums + (size_t)i * p.S_pad;
+        // thread handles coalitions tid, tid+256, ...; sixteen coefficients of E^T W y per pass over the rows
+        for (int k0 = 0; k0 < nA; k0 += 16) {
+            long long Tk[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Tk[k] = 0;
+#pragma unroll 2
+            for (int s = threadIdx.x; s < p.S; s += WLS_THREADS) {
+                const float2 a = sums[s];
+                double y;
+                if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(a.x, a.y, s_logtab) - lf1;
+                else y = (p.uniform_w ? (double)a.x * inv_n : (double)a.x) - f1;
+                const uint64_t zrow = p.z[s];
+                const bool zl = (zrow >> L) & 1ull;
+                const double v = p.w[s] * (y - (zl ? delta : 0.0));
+                const uint32_t zb = (uint32_t)((zl ? ~zrow : zrow) >> k0);
+                const long long vi = zl ? -to_fix(v) : to_fix(v);
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k0 + k < nA && ((zb >> k) & 1u)) Tk[k] += vi;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k0 + k < nA) {
+                    const long long r = warp_sum_ll(Tk[k]);
+                    if (lane == 0) s_part[wib][k0 + k] = r;
+                }
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nA) {
+            long long acc = 0;
+#pragma unroll
+            for (int wq = 0; wq < WLS_THREADS / 32; ++wq) acc += s_part[wq][threadIdx.x];
+            s_rhs[threadIdx.x] = from_fix(acc);
+        }
+        __syncthreads();
+        if (wib == 0) {
+            double sum = 0.0;
+            double beta[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < nA) {
+                    double b0 = 0.0, b1 = 0.0;      // two chains: the dot product is latency bound otherwise
+                    int l = 0;
+                    for (; l + 1 < nA; l += 2) {
+                        b0 = fma(s_ainv[k * nA + l], s_rhs[l], b0);
+                        b1 = fma(s_ainv[k * nA + l + 1], s_rhs[l + 1], b1);
+                    }
+                    if (l < nA) b0 = fma(s_ainv[k * nA + l], s_rhs[l], b0);
+                    beta[h] = b0 + b1;
+                    sum += beta[h];
+                }
+            }
+            sum = warp_sum(sum);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < G) {
+                    double val = k < nA ? beta[h] : delta - sum;       // the eliminated (last) group takes the remainder
+                    if (fabs(val) < 1e-10) val = 0.0;
+                    p.phi[slab + (size_t)i * G + k] = val;
+                    p.phi[(size_t)i * G + k] = (val == 0.0) ? 0.0 : -val;
+                }
+            }
+        }
+        // s_part / s_rhs are rewritten only after the next instance's row loop, which ends with __syncthreads
+    }
+}
+
+}  // namespace shared_path
+}  // namespace dks

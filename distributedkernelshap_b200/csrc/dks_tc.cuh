@@ -6,9 +6,10 @@
 // (scale = -kappa*log2 e, so exp(-kappa*score) = 2^T).  Z is 0/1 and exact in bf16; Delta is split into three bf16
 // terms (hi/mid/lo, ~fp32-exact) and accumulated in fp32 in TMEM by three tcgen05.mma (M=128, N=Npad, K=16).
 // Warp roles of the persistent CTA (one per SM):
-//   warps 0-3   producer group (one thread per tile row / background row): builds the instance's B operand (Delta
-//               splits) and each tile's A operand (Z bits expanded to bf16 through a 256-entry byte LUT, never read
-//               from HBM as a matrix) in shared memory; thread 0 issues the MMAs;
+//   warps 0-3   builders (one thread per tile row / background row): the instance's B operand (Delta splits) and each
+//               tile's A operand (Z bits expanded to bf16 through a 256-entry byte LUT, never read from HBM as a
+//               matrix) into shared memory, running up to four tiles ahead;
+//   warp 24     issuer: lane 0 waits for "A/B ready" and "accumulator free" and issues the three tcgen05.mma + commit;
 //   warps 4-19  epilogue, four groups of four warps = four TMEM accumulator buffers: tcgen05.ld the 128 x N scores,
 //               p1 = 1/(1+2^T), background-weighted sums (sum p1, sum p0) per coalition row -> shared memory;
 //   warps 20-23 WLS warpgroup, one instance behind (float64): y = link(ey) - link(fnull) per row folded into
@@ -32,6 +33,15 @@
 #ifndef DKS_TC_PREFETCH
 #define DKS_TC_PREFETCH 0       // 1: double-buffered tcgen05.ld and early accumulator release
 #endif
+#ifndef DKS_TC_EPI_WARPS
+#define DKS_TC_EPI_WARPS 16     // epilogue warps: 16 = four groups (one accumulator buffer each), 8 = two groups x two buffers
+#endif
+#ifndef DKS_TC_PINGPONG
+#define DKS_TC_PINGPONG 0       // 1: epilogue group pairs {0,1} / {2,3} alternate their compute phases (named barriers 3/4)
+#endif
+#ifndef DKS_TC_LOG_IN_WLS
+#define DKS_TC_LOG_IN_WLS 0     // 1: the epilogue hands (sum p1, sum p0) to the WLS warpgroup, which applies the link
+#endif
 
 namespace dks {
 namespace tc {
@@ -40,8 +50,10 @@ constexpr int TILE_S = 128;      // coalitions per MMA tile (UMMA M)
 constexpr int KP = 16;           // K per split: up to 15 varying groups + the constant column
 constexpr int NSPLIT = 3;        // bf16 hi/mid/lo
 constexpr int MAX_NPAD = 128;    // background rows per accumulator buffer (TMEM columns)
-constexpr int N_PROD_WARPS = 4, N_EPI_WARPS = 16, N_WLS_WARPS = 4;
-constexpr int NTHREADS = 32 * (N_PROD_WARPS + N_EPI_WARPS + N_WLS_WARPS);
+constexpr int N_PROD_WARPS = 4, N_EPI_WARPS = DKS_TC_EPI_WARPS, N_WLS_WARPS = 4;
+constexpr int N_GROUPS = N_EPI_WARPS / 4;   // epilogue groups; group k drains the tiles with g % N_GROUPS == k
+constexpr int ISSUER_WARP = N_PROD_WARPS + N_EPI_WARPS + N_WLS_WARPS;   // one more warp: its lane 0 issues the MMAs
+constexpr int NTHREADS = 32 * (ISSUER_WARP + 1);
 constexpr int NBUF = 4;          // accumulator / A-tile buffers: two per epilogue group
 constexpr int TMEM_COLS = 512;   // four accumulator buffers of 128 fp32 columns
 constexpr float T_CLAMP = 60.f;  // 2^t is clamped at 2^60 so the product of two (1 + 2^t) stays finite in fp32
@@ -105,6 +117,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -167,37 +182,39 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 
 // ---- shared memory carve-up ---------------------------------------------------------------------------------
 struct Smem {
-    uint64_t* bars;      // [12]: tmem_full[4], tmem_empty[4], inst_full[2], inst_empty[2]
+    uint64_t* bars;      // [18]: tmem_full[4], tmem_empty[4], inst_full[2], inst_empty[2], a_full[4], b_full[2]
     uint32_t* tmem_ptr;  // [1]
     int* vi;             // [16] varying position -> group (producer group only)
     double* chol;        // [15*15]
     double* rhs;         // [16]
-    double* part;        // [N_WLS_WARPS][16] per-warp partial right-hand sides
+    double* part;        // [N_WLS_WARPS][16] per-warp partial right-hand sides (int64 fixed point)
     double* ys;          // [2][S_cap] link(ey) - link(fnull) per coalition row, per instance parity
     float* wb;           // [MAX_NPAD] background weights
+    LogTabEntry* logtab; // [64] table of fast_log_ratio
     uint4* lut;          // [256] byte -> eight bf16 (1.0 / 0.0)
     unsigned char* A;    // [NBUF][128*KP*2]
     unsigned char* B;    // [2][NSPLIT][Npad*KP*2]
 };
 __host__ __device__ inline size_t smem_bytes(int S_cap, int Npad) {
-    return 128 /*bars + tmem ptr*/ + 16 * sizeof(int) + (15 * 15 + 16 + N_WLS_WARPS * 16) * sizeof(double) +
-           2 * (size_t)S_cap * sizeof(double) + MAX_NPAD * sizeof(float) + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
+    return 192 /*bars + tmem ptr*/ + 16 * sizeof(int) + (15 * 15 + 16 + N_WLS_WARPS * 16) * sizeof(double) +
+           2 * (size_t)S_cap * sizeof(double) + MAX_NPAD * sizeof(float) + DKS_LOGTAB_SIZE * 16 + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
            2 * NSPLIT * (size_t)Npad * KP * 2 + 64;
 }
 __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
     Smem s;
     s.bars = reinterpret_cast<uint64_t*>(base);
-    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 112);
-    s.vi = reinterpret_cast<int*>(base + 128);
-    s.chol = reinterpret_cast<double*>(base + 128 + 16 * sizeof(int));
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 160);
+    s.vi = reinterpret_cast<int*>(base + 192);
+    s.chol = reinterpret_cast<double*>(base + 192 + 16 * sizeof(int));
     s.rhs = s.chol + 15 * 15;
     s.part = s.rhs + 16;
     s.ys = s.part + N_WLS_WARPS * 16;
     s.wb = reinterpret_cast<float*>(s.ys + 2 * (size_t)S_cap);
     unsigned char* p = reinterpret_cast<unsigned char*>(s.wb + MAX_NPAD);
     p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    s.lut = reinterpret_cast<uint4*>(p);
-    s.A = p + 256 * 16;
+    s.logtab = reinterpret_cast<LogTabEntry*>(p);
+    s.lut = reinterpret_cast<uint4*>(p + DKS_LOGTAB_SIZE * 16);
+    s.A = p + DKS_LOGTAB_SIZE * 16 + 256 * 16;
     s.B = s.A + NBUF * (size_t)TILE_S * KP * 2;
     return s;
 }
@@ -210,6 +227,7 @@ struct TcParams {
     int uniform_w;
     float* dbg_T;          // optional [S_cap][Npad] dump of the scores of instance dbg_i
     int dbg_i;
+    float* dbg_time;       // optional [6][256] clock64 timeline of CTA 0 (debug kernel variant only)
     int ablate;            // bring-up aid (env DKS_TC_ABLATE, bit mask): knocks out one pipeline stage for timing
 };
 
@@ -287,18 +305,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
     uint64_t* tmem_empty = sm.bars + NBUF;
     uint64_t* inst_full = sm.bars + 2 * NBUF;
     uint64_t* inst_empty = sm.bars + 2 * NBUF + 2;
+    uint64_t* a_full = sm.bars + 2 * NBUF + 4;
+    uint64_t* b_full = sm.bars + 3 * NBUF + 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t slab = (size_t)p.n * G;
+    const int ninst = dks_inst_count(p);
+    if ((int)blockIdx.x >= ninst) return;        // nothing for this CTA (before any TMEM allocation)
 
     if (threadIdx.x == 0) {
         // arrivals are per warp (lane 0 after __syncwarp), not per thread
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4 * ARRIVALS_PER_WARP); }
         mbar_init(&inst_full[0], N_EPI_WARPS * ARRIVALS_PER_WARP); mbar_init(&inst_full[1], N_EPI_WARPS * ARRIVALS_PER_WARP);
         mbar_init(&inst_empty[0], N_WLS_WARPS * ARRIVALS_PER_WARP); mbar_init(&inst_empty[1], N_WLS_WARPS * ARRIVALS_PER_WARP);
+        for (int b = 0; b < NBUF; ++b) mbar_init(&a_full[b], 32 * N_PROD_WARPS);
+        mbar_init(&b_full[0], 32 * N_PROD_WARPS); mbar_init(&b_full[1], 32 * N_PROD_WARPS);
         fence_barrier_init();
     }
     // weights of the padded columns are zero; with uniform weights the sums stay unnormalised (weight 1)
     for (int j = threadIdx.x; j < MAX_NPAD; j += blockDim.x) sm.wb[j] = j < N ? (UW ? 1.f : p.wbf[j]) : 0.f;
+    if (threadIdx.x < DKS_LOGTAB_SIZE) logtab_fill(sm.logtab, threadIdx.x);
     for (int b = threadIdx.x; b < 256; b += blockDim.x) {
         uint4 e;
         e.x = ((b & 1) ? 0x00003F80u : 0u) | ((b & 2) ? 0x3F800000u : 0u);
@@ -308,12 +333,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         sm.lut[b] = e;
     }
     if (warp == 0) tmem_alloc(sm.tmem_ptr, TMEM_COLS);
+#if DKS_TC_PINGPONG
+    if (warp == 1) {   // total number of tiles this CTA will process (the ping-pong protocol needs whole rounds)
+        int cnt = 0;
+        for (int qi = blockIdx.x + lane * gridDim.x; qi < dks_inst_count(p); qi += 32 * gridDim.x) {
+            int M_, S_;
+            cnt += tiles_of(p, dks_inst_at(p, qi), M_, S_);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) sm.tmem_ptr[1] = (uint32_t)cnt;
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
 
     const uint32_t a_bytes = TILE_S * KP * 2, b_split_bytes = (uint32_t)Npad * KP * 2;
+    const long long t_start = clock64();
+    auto stamp = [&](int ev, uint32_t g) {   // debug timeline: event ev of tile g of CTA 0, in cycles since start
+        if (DBG && tp.dbg_time != nullptr && blockIdx.x == 0 && g < 256)
+            tp.dbg_time[ev * 256 + g] = (float)(clock64() - t_start);
+    };
 
     if (warp < N_PROD_WARPS) {
         // =================================== producer group / MMA issuer ===================================
@@ -368,10 +410,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 }
             }
         };
-        // next instance of this CTA (after i) that has tiles; -1 if none
-        auto next_work = [&](int i, int& Mn) {
-            for (int i2 = i + gridDim.x; i2 < p.n; i2 += gridDim.x) {
+        auto next_work = [&](int qi, int& Mn) {   // next instance of this CTA that has tiles (-1: none)
+            for (int q2 = qi + gridDim.x; q2 < ninst; q2 += gridDim.x) {
                 int S2;
+                const int i2 = dks_inst_at(p, q2);
                 if (tiles_of(p, i2, Mn, S2) > 0) return i2;
             }
             return -1;
@@ -380,17 +422,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         uint32_t g = 0;   // global tile counter of this CTA
         int qb = 0;       // ordinal among the instances that have tiles (selects the B slot)
         int built_for = -1;
-        for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
+        for (int qi = blockIdx.x; qi < ninst; qi += gridDim.x) {
+            const int i = dks_inst_at(p, qi);
             int M, S;
             const int T = tiles_of(p, i, M, S);
             if (T == 0) continue;
             const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : p.plans[M].z;
-            if (g >= 1) {  // every MMA issued so far has completed => the A/B buffers it read are free
-                uint32_t u = (g - 1) / NBUF;
-                mbar_wait_warp(&tmem_full[(g - 1) % NBUF], u & 1, p.status);
+            if (built_for != i) {            // only the first instance; later ones are prefetched below
+                build_B(i, M, qb & 1);
+                fence_proxy_async_smem();
+                mbar_arrive(&b_full[qb & 1]);
             }
-            if (built_for != i) build_B(i, M, qb & 1);      // only the first instance; later ones are prefetched below
-            unsigned char* Bq = sm.B + (size_t)(qb & 1) * NSPLIT * b_split_bytes;
+            const uint32_t g0 = g;
+            const int t_prefetch = T > NBUF - 1 ? NBUF - 1 : T - 1;   // after this tile: build the next instance's B
             for (int t = 0; t < T; ++t, ++g) {
                 const uint32_t buf = g % NBUF, u = g / NBUF;
                 const int s = t * TILE_S + ptid;
@@ -398,38 +442,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 if (s < S) zz = (uint32_t)(zp[s] & 0xFFFFull) | (1u << M);       // constant column carries score_j
                 if (g >= NBUF) mbar_wait_warp(&tmem_full[buf], (u - 1) & 1, p.status); // A[buf] free (MMA g-NBUF done)
                 unsigned char* Ab = sm.A + (size_t)buf * a_bytes;
-                if (!(tp.ablate & 16) || g < NBUF) {
-                    *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + ptid * 16) = sm.lut[zz & 0xFFu];
-                    *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + ptid * 16) = sm.lut[(zz >> 8) & 0xFFu];
-                    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-                    named_bar_sync(2, PROD_THREADS);
-                }
-                if (ptid == 0) {
-                    mbar_wait(&tmem_empty[buf], (u & 1) ^ 1, p.status);   // epilogue drained this accumulator
-                    tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(smem_u32(Ab), TILE_S * 16, 128);
-                    const uint32_t d_tmem = tmem_base + buf * 128;
-#pragma unroll
-                    for (int sp = 0; sp < ((tp.ablate & 2) ? 1 : NSPLIT); ++sp) {
-                        const uint64_t bdesc = make_smem_desc(smem_u32(Bq + sp * b_split_bytes), (uint32_t)Npad * 16, 128);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, sp > 0 ? 1u : 0u);
-                    }
-                    umma_commit(&tmem_full[buf]);   // arrives when the three MMAs have completed
-                }
-                // prefetch: while the epilogue chews on this instance, build the next instance's B operand.  Its slot
-                // was last read by the previous instance; MMAs complete in order, so once this instance's first MMA
-                // (just issued) has completed, that slot is free.
-                if (t == 0) {
+                *reinterpret_cast<uint4*>(Ab + 0 * (TILE_S * 16) + ptid * 16) = sm.lut[zz & 0xFFu];
+                *reinterpret_cast<uint4*>(Ab + 1 * (TILE_S * 16) + ptid * 16) = sm.lut[(zz >> 8) & 0xFFu];
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&a_full[buf]);
+                if (ptid == 0) stamp(0, g);                               // A tile ready
+                // prefetch: while this instance is in flight, build the next instance's B operand.  Its slot was last
+                // read by the previous instance; MMAs complete in order, so once this instance's first MMA has
+                // completed that slot is free.
+                if (t == t_prefetch) {
                     int Mn;
-                    int inext = next_work(i, Mn);
+                    int inext = next_work(qi, Mn);
                     if (inext >= 0) {
-                        mbar_wait_warp(&tmem_full[buf], u & 1, p.status);
+                        mbar_wait_warp(&tmem_full[g0 % NBUF], (g0 / NBUF) & 1, p.status);
                         build_B(inext, Mn, (qb + 1) & 1);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&b_full[(qb + 1) & 1]);
                         built_for = inext;
                     }
                 }
             }
             ++qb;
+        }
+    } else if (warp == ISSUER_WARP) {
+        // =================================== MMA issuer (one thread) ===================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(Npad);
+            uint64_t adesc[NBUF], bdesc[2][NSPLIT];
+#pragma unroll
+            for (int b = 0; b < NBUF; ++b) adesc[b] = make_smem_desc(smem_u32(sm.A + (size_t)b * a_bytes), TILE_S * 16, 128);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int sp = 0; sp < NSPLIT; ++sp)
+                    bdesc[sl][sp] = make_smem_desc(smem_u32(sm.B + ((size_t)sl * NSPLIT + sp) * b_split_bytes), (uint32_t)Npad * 16, 128);
+            uint32_t g = 0;
+            int qb = 0;
+            for (int qi = blockIdx.x; qi < ninst; qi += gridDim.x) {
+                const int i = dks_inst_at(p, qi);
+                int M, S;
+                const int T = tiles_of(p, i, M, S);
+                if (T == 0) continue;
+                const int slot = qb & 1;
+                mbar_wait(&b_full[slot], (qb >> 1) & 1, p.status);      // B operand of this instance is in place
+                for (int t = 0; t < T; ++t, ++g) {
+                    const uint32_t buf = g % NBUF, u = g / NBUF;
+                    mbar_wait(&a_full[buf], u & 1, p.status);             // A tile in place
+                    mbar_wait(&tmem_empty[buf], (u & 1) ^ 1, p.status);   // epilogue drained this accumulator
+                    stamp(1, g);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * 128;
+                    const int nsp = (tp.ablate & 2) ? 1 : NSPLIT;
+                    for (int sp = 0; sp < nsp; ++sp) {
+                        const uint64_t bd = slot ? bdesc[1][sp] : bdesc[0][sp];
+                        uint64_t ad = adesc[0];
+                        if (buf == 1) ad = adesc[1];
+                        if (buf == 2) ad = adesc[2];
+                        if (buf == 3) ad = adesc[3];
+                        umma_bf16(d_tmem, ad, bd, idesc, sp > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&tmem_full[buf]);   // arrives when the MMAs have completed
+                    stamp(2, g);
+                }
+                ++qb;
+            }
         }
     } else if (warp < N_PROD_WARPS + N_EPI_WARPS) {
         // =================================== epilogue ===================================
@@ -442,29 +518,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         const int nfull = N / 16;                     // accumulator chunks of 16 columns without padding
         const int ntail = N - nfull * 16;             // background rows in the last, partial chunk
         const int nchunks = nfull + (ntail ? 1 : 0);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 128;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const double lf1 = p.linkfnull[1], f1 = p.fnull[1];
         const float inv_n = 1.0f / (float)N;
 
+#if DKS_TC_PINGPONG
+        static_assert(DKS_TC_PINGPONG == 0 || N_GROUPS == 4, "ping-pong needs four epilogue groups");
+        const int pair = grp >> 1;                   // pairs {0,1} and {2,3} alternate compute phases
+        constexpr int PP_THREADS = 2 * 256;          // both pairs take part in each barrier (sync + arrive)
+        if (pair == 1) named_bar_arrive(3, PP_THREADS);   // pair 0 computes first
+        int my_rounds = 0;
+#endif
         uint32_t g = 0;
         int q = 0;
-        for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
+        for (int qi = blockIdx.x; qi < ninst; qi += gridDim.x, ++q) {
+            const int i = dks_inst_at(p, qi);
             int M, S;
             const int T = tiles_of(p, i, M, S);
             double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
             bool waited = false;
             for (int t = 0; t < T; ++t, ++g) {
-                if ((int)(g % NBUF) != grp) continue;
-                const uint32_t u = g / NBUF;
+                if ((int)(g % N_GROUPS) != grp) continue;
+                const uint32_t buf = g % NBUF, u = g / NBUF;
+                const uint32_t taddr = taddr0 + buf * 128;
                 const int s = t * TILE_S + row_in_tile;
-                mbar_wait_warp(&tmem_full[grp], u & 1, p.status);
+                if (quarter == 0 && lane == 0) stamp(3, g);               // epilogue group starts waiting
+                mbar_wait_warp(&tmem_full[buf], u & 1, p.status);
+#if DKS_TC_PINGPONG
+                named_bar_sync(3 + pair, PP_THREADS);                     // my pair's turn on the MUFU pipe
+                ++my_rounds;
+#endif
+                if (quarter == 0 && lane == 0) stamp(4, g);               // accumulator full seen
                 tc_fence_after();
                 float acc1 = 0.f, acc0 = 0.f;
 #if DKS_TC_PREFETCH
                 float va[16], vb[16];
                 auto release = [&]() {               // every chunk of this tile is in registers: free the accumulator
                     tc_fence_before();
-                    mbar_arrive_warp(&tmem_empty[grp]);
+                    mbar_arrive_warp(&tmem_empty[buf]);
                 };
                 if (tp.ablate & 8) {
 #pragma unroll
@@ -520,23 +611,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                     else consume_tail(v, sm.wb + c * 16, ntail, acc1, acc0);
                 }
                 tc_fence_before();
-                mbar_arrive_warp(&tmem_empty[grp]);  // accumulator buffer may be overwritten
+                mbar_arrive_warp(&tmem_empty[buf]);  // accumulator buffer may be overwritten
+                if (quarter == 0 && lane == 0) stamp(5, g);               // accumulator drained
+#endif
+#if DKS_TC_PINGPONG
+                // hand the MUFU pipe to the other pair (pair 1's arrival after the very last round has no taker)
+                if (!(pair == 1 && my_rounds == ((int)sm.tmem_ptr[1] + N_GROUPS - 1) / N_GROUPS))
+                    named_bar_arrive(3 + (pair ^ 1), PP_THREADS);
 #endif
                 if (!waited) {   // the row buffer of ordinal q-2 must have been consumed by the WLS warps
                     mbar_wait_warp(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
                     waited = true;
                 }
                 if (s < S && !(tp.ablate & 512)) {
+#if DKS_TC_LOG_IN_WLS
+                    reinterpret_cast<float2*>(ys)[s] = make_float2(acc1, acc0);   // link applied by the WLS warpgroup
+#else
                     // link(ey) - link(fnull); with the logit link the normalisation of the sums cancels
                     double y;
-                    if (p.link == DKS_LINK_LOGIT) y = log((double)acc1 / (double)acc0) - lf1;
+                    if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(acc1, acc0, sm.logtab) - lf1;
                     else y = (double)(UW ? acc1 * inv_n : acc1) - f1;
                     ys[s] = y;
+#endif
                 }
             }
             if (!waited) mbar_wait_warp(&inst_empty[q & 1], ((q >> 1) & 1) ^ 1, p.status);
             mbar_arrive_warp(&inst_full[q & 1]);     // release-arrive: publishes the rows written by this warp
         }
+#if DKS_TC_PINGPONG
+        {   // groups without a tile in the last (partial) round still take part in its barriers
+            const int rounds = ((int)sm.tmem_ptr[1] + N_GROUPS - 1) / N_GROUPS;
+            while (my_rounds < rounds) {
+                named_bar_sync(3 + pair, PP_THREADS);
+                ++my_rounds;
+                if (!(pair == 1 && my_rounds == rounds)) named_bar_arrive(3 + (pair ^ 1), PP_THREADS);
+            }
+        }
+#endif
     } else {
         // =================================== WLS warpgroup (float64) ===================================
         // per row: y = link(ey) - link(fnull) from the (sum p1, sum p0) pair, folded into E^T W y; then the
@@ -547,7 +658,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         int cachedM = -1;
         bool have_inverse = false;
         int q = 0;
-        for (int i = blockIdx.x; i < p.n; i += gridDim.x, ++q) {
+        for (int qi = blockIdx.x; qi < ninst; qi += gridDim.x, ++q) {
+            const int i = dks_inst_at(p, qi);
             int M, S;
             const int T = tiles_of(p, i, M, S);
             const int C = p.C;
@@ -600,33 +712,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             const double delta = p.dlink[(size_t)i * C + 1];
             mbar_wait_warp(&inst_full[q & 1], (q >> 1) & 1, p.status);
             const double* ys = sm.ys + (size_t)(q & 1) * p.S_cap;
-            double Tk[KP - 1];
+            long long Tk[KP - 1];                    // fixed-point partial sums of E^T W y (exact integer adds)
 #pragma unroll
-            for (int k = 0; k < KP - 1; ++k) Tk[k] = 0.0;
+            for (int k = 0; k < KP - 1; ++k) Tk[k] = 0;
+#if DKS_TC_LOG_IN_WLS
+            const double lf1 = p.linkfnull[1], f1 = p.fnull[1], inv_n = 1.0 / (double)N;
+#endif
             for (int s = wtid; s < ((tp.ablate & 4) ? 0 : S); s += WLS_THREADS) {
+#if DKS_TC_LOG_IN_WLS
+                const float2 a = reinterpret_cast<const float2*>(ys)[s];
+                double y;
+                if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(a.x, a.y, sm.logtab) - lf1;
+                else y = (UW ? (double)a.x * inv_n : (double)a.x) - f1;
+#else
                 const double y = ys[s];
+#endif
                 const uint64_t zrow = zp[s];
                 const double wrow = wp[s];
                 // fold the row into E^T W y:  e_k = z_k - z_L = (z_L ? -1 : 1) * z'_k with z' = z_L ? ~z : z
                 const bool zl = (zrow >> L) & 1ull;
-                double v = wrow * (y - (zl ? delta : 0.0));
+                const double v = wrow * (y - (zl ? delta : 0.0));
                 const uint32_t zb = (uint32_t)(zl ? ~zrow : zrow);
-                if (zl) v = -v;
+                const long long vi = zl ? -to_fix(v) : to_fix(v);
 #pragma unroll
                 for (int k = 0; k < KP - 1; ++k)
-                    if (k < nA && ((zb >> k) & 1u)) Tk[k] += v;
+                    if (k < nA && ((zb >> k) & 1u)) Tk[k] += vi;
             }
+            long long* part_ll = reinterpret_cast<long long*>(sm.part);
 #pragma unroll
             for (int k = 0; k < KP - 1; ++k)
                 if (k < nA && !(tp.ablate & 128)) {
-                    double r = warp_sum(Tk[k]);
-                    if (lane == 0) sm.part[ww * 16 + k] = r;
+                    const long long r = warp_sum_ll(Tk[k]);
+                    if (lane == 0) part_ll[ww * 16 + k] = r;
                 }
             named_bar_sync(1, WLS_THREADS);
-            if (wtid < nA) {                              // fixed summation order: deterministic results
-                double acc = 0.0;
-                for (int e = 0; e < N_WLS_WARPS; ++e) acc += sm.part[e * 16 + wtid];
-                sm.rhs[wtid] = acc;
+            if (wtid < nA) {
+                long long acc = 0;
+                for (int e = 0; e < N_WLS_WARPS; ++e) acc += part_ll[e * 16 + wtid];
+                sm.rhs[wtid] = from_fix(acc);
             }
             named_bar_sync(1, WLS_THREADS);
             if (have_inverse) {
@@ -695,6 +818,7 @@ inline int tc_launch(dks_ctx* ctx, const ExplainParams& p) {
     tp.uniform_w = ctx->uniform_w ? 1 : 0;
     tp.dbg_T = ctx->dbg_T;
     tp.dbg_i = ctx->dbg_i;
+    tp.dbg_time = ctx->dbg_time;
     const char* ab = getenv("DKS_TC_ABLATE");
     tp.ablate = ab ? atoi(ab) : 0;
     size_t smem = tc::smem_bytes(p.S_cap, tp.Npad);

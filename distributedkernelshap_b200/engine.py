@@ -113,7 +113,8 @@ class GpuKernelExplainer:
         return out
 
     def set_kernel(self, kernel):
-        code = {"auto": _cabi.KERNEL_AUTO, "simt": _cabi.KERNEL_SIMT, "tcgen05": _cabi.KERNEL_TCGEN05}[kernel]
+        code = {"auto": _cabi.KERNEL_AUTO, "simt": _cabi.KERNEL_SIMT, "tcgen05": _cabi.KERNEL_TCGEN05,
+                "shared": _cabi.KERNEL_SHARED}[kernel]
         _cabi.check(self.lib.dks_set_kernel(self._ctx, code))
         self.kernel = kernel
 
@@ -304,6 +305,18 @@ class GpuKernelExplainer:
         finally:
             _cabi.check(self.lib.dks_debug_score_dump(self._ctx, -1))
         return buf[:rows.value * cols.value].reshape(rows.value, cols.value).copy()
+
+    def debug_timeline(self, X, nsamples="auto"):
+        """clock64 timeline [6, 256] of CTA 0 of the tcgen05 kernel (see ``dks_debug_get_timeline``); tests/tuning only."""
+        self.shap_values(X, nsamples=nsamples, l1_reg=False)          # plans uploaded, steady state
+        _cabi.check(self.lib.dks_debug_score_dump(self._ctx, 0))
+        try:
+            self.shap_values(X, nsamples=nsamples, l1_reg=False)
+            buf = np.zeros((6, 256), dtype=np.float32)
+            _cabi.check(self.lib.dks_debug_get_timeline(self._ctx, _cabi.ptr(buf)))
+        finally:
+            _cabi.check(self.lib.dks_debug_score_dump(self._ctx, -1))
+        return buf
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

@@ -49,6 +49,8 @@ extern "C" {
 #define DKS_KERNEL_AUTO 0
 #define DKS_KERNEL_SIMT 1       /* CUDA-core kernel (all shapes) */
 #define DKS_KERNEL_TCGEN05 2    /* tensor-core kernel: Z tile x background tile on tcgen05/TMEM */
+#define DKS_KERNEL_SHARED 3     /* shared-plan fast path for instances whose groups all vary (+ best general kernel
+                                 * for the rest); DKS_KERNEL_AUTO picks it whenever it applies */
 
 typedef struct dks_ctx dks_ctx;
 
@@ -133,6 +135,9 @@ int dks_last_timings(dks_ctx* ctx, float* ms3);
  * (synchronises); rows/cols report its shape. */
 int dks_debug_score_dump(dks_ctx* ctx, int instance);
 int dks_debug_get_scores(dks_ctx* ctx, float* out_host, int max_floats, int* rows, int* cols);
+/* cycle timeline of CTA 0 recorded by the same debug run: float32 [6][256], event e of tile g at [e*256+g]
+ * (0 A-tile ready, 1 accumulator free, 2 MMAs issued, 3 epilogue waits, 4 accumulator full, 5 accumulator drained) */
+int dks_debug_get_timeline(dks_ctx* ctx, float* out_host);
 
 #ifdef __cplusplus
 }

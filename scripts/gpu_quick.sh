@@ -3,4 +3,4 @@
 OUT=gpurun_out/${1:-quick}
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest.log
-timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/bench.log
+for k in auto tcgen05; do timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --kernel $k 2>&1 | tail -1 | tee -a $OUT/bench.log; done

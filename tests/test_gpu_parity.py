@@ -25,7 +25,7 @@ def _engine(prob, link="logit", predict="predict_proba", **kw):
     return GpuKernelExplainer(getattr(prob["clf"], predict), dd, link=link, **kw)
 
 
-KERNELS = ["simt", "tcgen05"]
+KERNELS = ["simt", "tcgen05", "auto"]      # auto = shared-plan fast path where it applies + tcgen05 for the rest
 
 
 def _compare(got, want, tol=TOL):
@@ -255,6 +255,7 @@ def test_tcgen05_and_simt_kernels_agree_and_many_instances_per_cta():
         eng = _engine(prob, kernel=kernel)
         res[kernel] = eng.shap_values(prob["X"], l1_reg=False)          # nsamples='auto' = 2072
     assert rel_err(res["tcgen05"][1], res["simt"][1]) < 2e-6
+    assert rel_err(res["auto"][1], res["simt"][1]) < 2e-6
 
 
 def test_golden_fixtures_on_gpu():
@@ -267,7 +268,7 @@ def test_golden_fixtures_on_gpu():
         clf = LinearSoftmaxClassifier(g["coef"], g["intercept"], multi_class=str(g["multi_class"]))
         prob = dict(X=g["X"], bg=g["bg"], groups=groups, group_names=[f"g{i}" for i in range(len(groups))], clf=clf,
                     weights=g["weights"])
-        for kernel in (KERNELS if len(groups) <= 15 else ["simt"]):
+        for kernel in (KERNELS if len(groups) <= 15 else ["simt", "auto"]):
             eng = _engine(prob, link=str(g["link"]), kernel=kernel)
             plans = None if g["full"] else [(g["Z"][i], g["w"][i]) for i in range(g["X"].shape[0])]
             got = eng.shap_values(g["X"], nsamples=int(g["nsamples"]), l1_reg=False, plans=plans)
