@@ -436,9 +436,9 @@ class KernelShap(Explainer, FitMixin):
         if self.summarise_result:
             shap_values = [sum_categories(arr, cat_vars_start_idx, cat_vars_enc_dim) for arr in shap_values]
 
-        # raw predictions on the scale the explainer works in
-        linkfv = np.vectorize(convert_to_link(self.link).f)
-        raw_predictions = linkfv(self.predictor(X))
+        # raw predictions on the scale the explainer works in (the reference wraps link.f in np.vectorize, an
+        # interpreted per-element loop; both links are NumPy ufunc expressions, so they are applied to the array)
+        raw_predictions = convert_to_link(self.link).f(np.asarray(self.predictor(X), dtype=np.float64))
 
         argmax_pred = np.argmax(np.atleast_2d(raw_predictions), axis=1) if self.task != 'regression' else []
         importances = rank_by_importance(shap_values, feature_names=self.feature_names)

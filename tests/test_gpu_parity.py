@@ -277,3 +277,56 @@ def test_golden_fixtures_on_gpu():
             if g["full"]:
                 assert rel_err(got[1], g["phi_exact"][:, :, 1]) < TOL
             np.testing.assert_allclose(eng.expected_value, g["expected_value"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomized_shapes_all_kernels(seed):
+    """Random group structures / background sizes / sample budgets / weights through every kernel that supports them."""
+    rng = np.random.default_rng(1000 + seed)
+    G = int(rng.choice([2, 3, 5, 8, 12, 15, 16, 23, 40]))
+    widths = tuple(int(w) for w in rng.integers(1, 4, size=G))
+    N = int(rng.choice([1, 7, 16, 31, 32, 64, 100, 127, 128, 150]))
+    n = int(rng.integers(3, 40))
+    weights = bool(rng.integers(0, 2))
+    nsamples = int(rng.choice([50, 128, 257, 500, 1000]))
+    const = tuple(int(g) for g in rng.choice(G, size=int(rng.integers(0, max(1, G // 3))), replace=False)) if G > 3 else ()
+    prob = make_problem(seed=2000 + seed, n=n, N=N, widths=widths, kappa=float(rng.choice([1.0, 2.0])), weights=weights,
+                        constant_groups=const)
+    link = str(rng.choice(["logit", "identity"]))
+    orc = _oracle(prob, link)
+    np.random.seed(seed)
+    want = orc.shap_values(prob["X"], nsamples=nsamples, l1_reg=False)
+    plans = [(Z, w) if Z is not None else None for (_, Z, w) in orc.plans]
+    kernels = ["simt", "auto"] + (["tcgen05"] if G <= 15 and N <= 128 else [])
+    for kernel in kernels:
+        eng = _engine(prob, link, kernel=kernel)
+        got = eng.shap_values(prob["X"], nsamples=nsamples, l1_reg=False, plans=plans)      # oracle's per-instance plans
+        _compare(got, want)
+        np.random.seed(77)
+        shared = eng.shap_values(prob["X"], nsamples=nsamples, l1_reg=False)                # engine's shared plans
+        fx = prob["clf"].predict_proba(prob["X"])
+        lf = orc.link.f
+        np.testing.assert_allclose(shared[1].sum(1), lf(fx[:, 1]) - eng.expected_value[1], rtol=1e-7, atol=1e-8)
+    # shared plans: every kernel draws the same plan from the same stream state => same values
+    res = []
+    for kernel in kernels:
+        np.random.seed(77)
+        res.append(_engine(prob, link, kernel=kernel).shap_values(prob["X"], nsamples=nsamples, l1_reg=False)[1])
+    for r in res[1:]:
+        assert rel_err(r, res[0]) < 5e-6
+
+
+def test_config2_shape_64_features_bg512():
+    """BASELINE configs[2] shape at reduced n: 64 ungrouped features, 512 background rows, nsamples 4096."""
+    from distributedkernelshap_b200.datasets import dense_tabular
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from oracle.shap_kernel_oracle import KernelExplainerOracle
+    d = dense_tabular(n=6, n_features=64, n_background=512, seed=0)
+    orc = KernelExplainerOracle(d["predictor"].predict_proba, d["background"], link="logit", record_plans=True)
+    np.random.seed(0)
+    want = orc.shap_values(d["X_explain"], nsamples=4096, l1_reg=False)
+    eng = GpuKernelExplainer(d["predictor"].predict_proba, d["background"], link="logit")
+    got = eng.shap_values(d["X_explain"], nsamples=4096, l1_reg=False, plans=[(Z, w) for (_, Z, w) in orc.plans])
+    _compare(got, want)
+    with pytest.raises(NotImplementedError):          # reference default l1_reg='auto' would select features here
+        eng.shap_values(d["X_explain"], nsamples=4096)
