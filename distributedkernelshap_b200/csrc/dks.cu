@@ -160,8 +160,23 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         wp.uniform_w = 1; wp.sums = ctx->d_sums; wp.z = pg.z; wp.w = pg.w; wp.ainv = pg.ainv; wp.dlink = ctx->d_dlink;
         wp.linkfnull = ctx->d_linkfnull; wp.fnull = ctx->d_fnull; wp.list = ctx->d_idx_full; wp.count = ctx->d_counts;
         wp.phi = phi_dev;
-        int wgrid = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;     // persistent: ~4 CTAs of 8 warps per SM
-        dks::shared_path::wls_shared_kernel<<<wgrid, dks::shared_path::WLS_THREADS, 0, ctx->stream>>>(wp);
+        if (pg.pmat != nullptr) {
+            dks::shared_path::WlsPmatParams pp;
+            pp.n = n; pp.N = ctx->N; pp.G = G; pp.C = ctx->C; pp.S = S; pp.S_pad = S_pad; pp.link = ctx->link; pp.uniform_w = 1;
+            pp.sums = ctx->d_sums; pp.pmat = pg.pmat; pp.dvec = pg.dvec; pp.dlink = ctx->d_dlink;
+            pp.linkfnull = ctx->d_linkfnull; pp.fnull = ctx->d_fnull; pp.list = ctx->d_idx_full; pp.count = ctx->d_counts;
+            pp.phi = phi_dev;
+            size_t psm = dks::shared_path::wls_pmat_smem(G, S_pad);
+            CUDA_TRY(cudaFuncSetAttribute(dks::shared_path::wls_pmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+            int per_sm = (int)((size_t)ctx->max_smem_optin / (psm + 8192));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;
+            int pgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;
+            dks::shared_path::wls_pmat_kernel<<<pgrid, dks::shared_path::PMAT_THREADS, psm, ctx->stream>>>(pp);
+        } else {
+            int wgrid = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;     // persistent: ~4 CTAs of 8 warps per SM
+            dks::shared_path::wls_shared_kernel<<<wgrid, dks::shared_path::WLS_THREADS, 0, ctx->stream>>>(wp);
+        }
         ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
         p.list = ctx->d_idx_other;      // the general kernel below takes the remaining instances
@@ -516,6 +531,20 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         ctx->launches += 1;
         CUDA_TRY(cudaGetLastError());
         pd.dmT = dm;
+        // projection form of the solve: P = inv(E^T W E) E^T W and d = P z_L
+        if (M - 1 <= dks::shared_path::PMAT_MAXK &&
+            dks::shared_path::wls_pmat_smem(M, pd.S_pad) + 8192 <= (size_t)ctx->max_smem_optin) {
+            float* pm = nullptr; double* dv = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&pm, sizeof(float) * (size_t)(M - 1) * pd.S_pad));
+            CUDA_TRY(cudaMalloc((void**)&dv, sizeof(double) * (M - 1)));
+            ctx->plan_allocs.push_back(pm); ctx->plan_allocs.push_back(dv);
+            long long tot = (long long)(M - 1) * pd.S_pad;
+            dks::shared_path::plan_pmat_kernel<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(dz, dw, di, S, pd.S_pad, M, pm);
+            dks::shared_path::plan_dvec_kernel<<<M - 1, 32, 0, ctx->stream>>>(dz, pm, S, pd.S_pad, M, dv);
+            ctx->launches += 2;
+            CUDA_TRY(cudaGetLastError());
+            pd.pmat = pm; pd.dvec = dv;
+        }
     }
     ctx->h_plans[M] = pd;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));

@@ -18,6 +18,8 @@ struct PlanDev {
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
     const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
     const float* dmT;    // [N][S_pad] 2^(scaled background part of the score) for the full varying set (shared fast path)
+    const float* pmat;   // [(M-1)][S_pad] P = inv(E^T W E) E^T W (float32): beta = P y - delta * dvec
+    const double* dvec;  // [(M-1)] P z_L
     int S;
     int S_pad;
 };

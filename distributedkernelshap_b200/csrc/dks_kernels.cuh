@@ -30,8 +30,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// ---- cheap link arithmetic.  Vector FP64 runs at ~16 lanes/clk/SM on this part (as scarce as MUFU), so the per-row
-// work avoids it: the log is evaluated in fp32 around a 64-entry table, and E^T W y is accumulated in fixed point.
+// ---- cheap link arithmetic.  Measured on B200 (scripts/probes/fp64_probe.cu): DFMA/DADD 64 lanes/clk/SM, but
+// f32<->f64 conversions only ~16 (they share the XU pipe with MUFU) and a float64 division + log() is a ~110-instruction
+// dependent chain.  So the per-row log is evaluated in fp32 around a 64-entry table with two float64 ops at the end.
 //
 // ln(a1) - ln(a0) for positive float32 sums.  a = 2^e * m, m in [1,2) = c_k (1 + r) with c_k = 1 + (k + 1/2)/64 the centre
 // of the k-th of 64 mantissa intervals, |r| <= 2^-7.  r = m/c_k - 1 is formed with a two-float reciprocal
@@ -60,7 +61,8 @@ __device__ __forceinline__ double fast_log_ratio(float a1, float a0, const LogTa
 }
 
 // fixed-point accumulation of E^T W y: v -> round(v * 2^40) as int64 (|v| = w |y| < 8e6 fits), integer adds are exact and
-// order-independent (bit-reproducible whatever the reduction order); resolution 2^-40 ~ 9e-13 per row.
+// order-independent (bit-reproducible whatever the reduction order); resolution 2^-40 ~ 9e-13 per row.  (64-bit integer
+// adds run at ~30 lanes/clk/SM, half the DADD rate: used where order-independence matters, not for speed.)
 #define DKS_FIX_SCALE 1099511627776.0          /* 2^40 */
 #define DKS_FIX_INV 9.094947017729282379150390625e-13   /* 2^-40 */
 __device__ __forceinline__ long long to_fix(double v) { return __double2ll_rn(v * DKS_FIX_SCALE); }

@@ -179,6 +179,129 @@ struct WlsSharedParams {
     double* phi;             // [C][n][G]
 };
 
+// ---- projection form of the solve for a shared plan ----------------------------------------------------------------
+// beta = inv(A) E^T W (y - z_L delta) = P y - delta d,  P[k][s] = w_s sum_l inv(A)[k][l] (z_sl - z_sL),  d = P z_L.
+// P depends only on the plan: computed once (float32 copy for the kernel, float64 for d).
+__global__ void plan_pmat_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w,
+                                 const double* __restrict__ ainv, int S, int S_pad, int M, float* __restrict__ pmat) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nA = M - 1, L = M - 1;
+    if (idx >= nA * S_pad) return;
+    const int k = idx / S_pad, s = idx - k * S_pad;
+    double acc = 0.0;
+    if (s < S) {
+        const uint64_t zz = z[s];
+        const int zl = (int)((zz >> L) & 1ull);
+        for (int l = 0; l < nA; ++l) {
+            const int e = (int)((zz >> l) & 1ull) - zl;
+            if (e) acc += ainv[k * nA + l] * (double)e;
+        }
+        acc *= w[s];
+    }
+    pmat[idx] = (float)acc;
+}
+__global__ void plan_dvec_kernel(const uint64_t* __restrict__ z, const float* __restrict__ pmat, int S, int S_pad, int M,
+                                 double* __restrict__ dvec) {
+    // d = P z_L with the SAME float32 P the kernel multiplies y by, so the delta term is removed consistently
+    const int k = blockIdx.x, nA = M - 1, L = M - 1;
+    if (k >= nA) return;
+    double acc = 0.0;
+    for (int s = threadIdx.x; s < S; s += 32)
+        if ((z[s] >> L) & 1ull) acc += (double)pmat[(size_t)k * S_pad + s];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) dvec[k] = acc;
+}
+
+struct WlsPmatParams {
+    int n, N, G, C, S, S_pad, link, uniform_w;
+    const float2* sums;
+    const float* pmat;       // [(G-1)][S_pad]
+    const double* dvec;      // [(G-1)]
+    const double* dlink;
+    const double* linkfnull;
+    const double* fnull;
+    const int* list;
+    const int* count;
+    double* phi;
+};
+constexpr int PMAT_THREADS = 256;
+constexpr int PMAT_MAXK = 24;        // coefficients held in registers per thread
+inline size_t wls_pmat_smem(int G, int S_pad) { return (size_t)(G - 1) * S_pad * sizeof(float); }
+
+// Persistent CTAs; P resident in shared memory.  Per coalition row: y, then nA multiply-adds in float64.
+__global__ void __launch_bounds__(PMAT_THREADS) wls_pmat_kernel(WlsPmatParams p) {
+    extern __shared__ float s_P[];                       // [(G-1)][S_pad]
+    __shared__ double s_part[PMAT_THREADS / 32][PMAT_MAXK];
+    __shared__ LogTabEntry s_logtab[DKS_LOGTAB_SIZE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int G = p.G, nA = G - 1;
+    const int cnt = *p.count;
+    if ((int)blockIdx.x >= cnt) return;
+    if (threadIdx.x < DKS_LOGTAB_SIZE) logtab_fill(s_logtab, threadIdx.x);
+    for (int idx = threadIdx.x; idx < nA * p.S_pad; idx += PMAT_THREADS) s_P[idx] = p.pmat[idx];
+    __syncthreads();
+    const double lf1 = p.linkfnull[1], f1 = p.fnull[1], inv_n = 1.0 / (double)p.N;
+    const size_t slab = (size_t)p.n * G;
+    int i_next = p.list[blockIdx.x];
+    double delta_next = p.dlink[(size_t)i_next * p.C + 1];
+    for (int m = blockIdx.x; m < cnt; m += gridDim.x) {
+        const int i = i_next;
+        const double delta = delta_next;
+        if (m + (int)gridDim.x < cnt) {            // next instance's index and delta: off the critical path
+            i_next = p.list[m + gridDim.x];
+            delta_next = p.dlink[(size_t)i_next * p.C + 1];
+        }
+        const float2* sums = p.sums + (size_t)i * p.S_pad;
+        double Tk[PMAT_MAXK];
+#pragma unroll
+        for (int k = 0; k < PMAT_MAXK; ++k) Tk[k] = 0.0;
+        for (int s0 = 0; s0 < p.S; s0 += 8 * PMAT_THREADS) {
+            float2 a[8];                               // eight independent loads in flight per thread
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int s = s0 + r * PMAT_THREADS + threadIdx.x;
+                a[r] = s < p.S ? sums[s] : make_float2(1.f, 1.f);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int s = s0 + r * PMAT_THREADS + threadIdx.x;
+                if (s < p.S) {
+                    double y;
+                    if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(a[r].x, a[r].y, s_logtab) - lf1;
+                    else y = (p.uniform_w ? (double)a[r].x * inv_n : (double)a[r].x) - f1;
+#pragma unroll
+                    for (int k = 0; k < PMAT_MAXK; ++k)
+                        if (k < nA) Tk[k] = fma((double)s_P[(size_t)k * p.S_pad + s], y, Tk[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PMAT_MAXK; ++k) {
+            if (k < nA) {
+                const double r = warp_sum(Tk[k]);
+                if (lane == 0) s_part[wib][k] = r;
+            }
+        }
+        __syncthreads();
+        if (wib == 0) {
+            double beta = 0.0;
+            if (lane < nA) {
+#pragma unroll
+                for (int wq = 0; wq < PMAT_THREADS / 32; ++wq) beta += s_part[wq][lane];      // fixed order: reproducible
+                beta -= delta * p.dvec[lane];
+            }
+            const double sum = warp_sum(beta);
+            if (lane < G) {
+                double val = lane < nA ? beta : delta - sum;       // the eliminated (last) group takes the remainder
+                if (fabs(val) < 1e-10) val = 0.0;
+                p.phi[slab + (size_t)i * G + lane] = val;
+                p.phi[(size_t)i * G + lane] = (val == 0.0) ? 0.0 : -val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Persistent CTAs of 8 warps, each looping over instances: y = link(ey) - link(fnull) per coalition, E^T W y in 2^-40
 // fixed point (integer adds: exact, order-independent), beta = inv(E^T W E) (E^T W y), phi.
 constexpr int WLS_THREADS = 256;
