@@ -499,8 +499,11 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_shared_plan: M=%d out of [2,%d]", M, DKS_MAX_GROUPS);
     REQUIRE(S >= 1 && zbits_host && w_host, "dks_set_shared_plan: bad arguments");
     uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr; double* di = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S));
-    CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S));
+    const size_t S_even = ((size_t)S + 1) & ~(size_t)1;     // TMA bulk copies move 16-byte multiples
+    CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S_even));
+    CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S_even));
+    CUDA_TRY(cudaMemsetAsync(dz, 0, sizeof(uint64_t) * S_even, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(double) * S_even, ctx->stream));
     CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
     CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
     ctx->plan_allocs.push_back(dz); ctx->plan_allocs.push_back(dw); ctx->plan_allocs.push_back(dc);

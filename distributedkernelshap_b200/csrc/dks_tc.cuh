@@ -110,6 +110,15 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
 #endif
 }
 constexpr uint32_t ARRIVALS_PER_WARP = DKS_TC_WARP_ARRIVE ? 1u : 32u;
+// TMA bulk copy global -> shared (1-D, cp.async.bulk), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -182,7 +191,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 
 // ---- shared memory carve-up ---------------------------------------------------------------------------------
 struct Smem {
-    uint64_t* bars;      // [18]: tmem_full[4], tmem_empty[4], inst_full[2], inst_empty[2], a_full[4], b_full[2]
+    uint64_t* bars;      // [19]: tmem_full[4], tmem_empty[4], inst_full[2], inst_empty[2], a_full[4], b_full[2], plan_ready
     uint32_t* tmem_ptr;  // [1]
     int* vi;             // [16] varying position -> group (producer group only)
     double* chol;        // [15*15]
@@ -190,6 +199,8 @@ struct Smem {
     double* part;        // [N_WLS_WARPS][16] per-warp partial right-hand sides (int64 fixed point)
     double* ys;          // [2][S_cap] link(ey) - link(fnull) per coalition row, per instance parity
     float* wb;           // [MAX_NPAD] background weights
+    uint64_t* zs;        // [S_cap] coalition words of the staged shared plan (TMA bulk copy)
+    double* ws;          // [S_cap] its kernel weights
     LogTabEntry* logtab; // [64] table of fast_log_ratio
     uint4* lut;          // [256] byte -> eight bf16 (1.0 / 0.0)
     unsigned char* A;    // [NBUF][128*KP*2]
@@ -197,13 +208,14 @@ struct Smem {
 };
 __host__ __device__ inline size_t smem_bytes(int S_cap, int Npad) {
     return 192 /*bars + tmem ptr*/ + 16 * sizeof(int) + (15 * 15 + 16 + N_WLS_WARPS * 16) * sizeof(double) +
-           2 * (size_t)S_cap * sizeof(double) + MAX_NPAD * sizeof(float) + DKS_LOGTAB_SIZE * 16 + 256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
+           2 * (size_t)S_cap * sizeof(double) + 2 * ((size_t)S_cap + 2) * 8 + MAX_NPAD * sizeof(float) + DKS_LOGTAB_SIZE * 16 +
+           256 * 16 + NBUF * (size_t)TILE_S * KP * 2 +
            2 * NSPLIT * (size_t)Npad * KP * 2 + 64;
 }
 __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
     Smem s;
     s.bars = reinterpret_cast<uint64_t*>(base);
-    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 160);
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(base + 168);
     s.vi = reinterpret_cast<int*>(base + 192);
     s.chol = reinterpret_cast<double*>(base + 192 + 16 * sizeof(int));
     s.rhs = s.chol + 15 * 15;
@@ -212,6 +224,10 @@ __device__ inline Smem carve(unsigned char* base, int S_cap, int Npad) {
     s.wb = reinterpret_cast<float*>(s.ys + 2 * (size_t)S_cap);
     unsigned char* p = reinterpret_cast<unsigned char*>(s.wb + MAX_NPAD);
     p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    const size_t plan_words = ((size_t)S_cap + 1) & ~(size_t)1;          // 16-byte multiples for the bulk copy
+    s.zs = reinterpret_cast<uint64_t*>(p);
+    s.ws = reinterpret_cast<double*>(p + plan_words * 8);
+    p += 2 * plan_words * 8;
     s.logtab = reinterpret_cast<LogTabEntry*>(p);
     s.lut = reinterpret_cast<uint4*>(p + DKS_LOGTAB_SIZE * 16);
     s.A = p + DKS_LOGTAB_SIZE * 16 + 256 * 16;
@@ -307,6 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
     uint64_t* inst_empty = sm.bars + 2 * NBUF + 2;
     uint64_t* a_full = sm.bars + 2 * NBUF + 4;
     uint64_t* b_full = sm.bars + 3 * NBUF + 4;
+    uint64_t* plan_ready = sm.bars + 3 * NBUF + 6;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t slab = (size_t)p.n * G;
     const int ninst = dks_inst_count(p);
@@ -319,6 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
         mbar_init(&inst_empty[0], N_WLS_WARPS * ARRIVALS_PER_WARP); mbar_init(&inst_empty[1], N_WLS_WARPS * ARRIVALS_PER_WARP);
         for (int b = 0; b < NBUF; ++b) mbar_init(&a_full[b], 32 * N_PROD_WARPS);
         mbar_init(&b_full[0], 32 * N_PROD_WARPS); mbar_init(&b_full[1], 32 * N_PROD_WARPS);
+        mbar_init(plan_ready, 1);
         fence_barrier_init();
     }
     // weights of the padded columns are zero; with uniform weights the sums stay unnormalised (weight 1)
@@ -349,6 +367,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_ptr;
+
+    // Stage the shared plan of this CTA's first instance (coalition words + weights) into shared memory with two TMA
+    // bulk copies; builders and WLS warps read it from there instead of re-reading global memory every tile.
+    // Instances with another M (rare) and per-instance plans keep reading global memory.
+    int staged_M = -1;
+    if (p.ext_z == nullptr) {
+        for (int qi = blockIdx.x; qi < ninst && staged_M < 0; qi += gridDim.x) {
+            int M_, S_;
+            if (tiles_of(p, dks_inst_at(p, qi), M_, S_) > 0) staged_M = M_;
+        }
+        if (staged_M >= 0) {
+            const uint32_t bytes = (uint32_t)((((size_t)p.plans[staged_M].S + 1) & ~(size_t)1) * 8);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(plan_ready, 2 * bytes);
+                tma_load_1d(sm.zs, p.plans[staged_M].z, bytes, plan_ready);
+                tma_load_1d(sm.ws, p.plans[staged_M].w, bytes, plan_ready);
+            }
+            mbar_wait(plan_ready, 0, p.status);
+        }
+    }
 
     const uint32_t a_bytes = TILE_S * KP * 2, b_split_bytes = (uint32_t)Npad * KP * 2;
     const long long t_start = clock64();
@@ -427,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             int M, S;
             const int T = tiles_of(p, i, M, S);
             if (T == 0) continue;
-            const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : p.plans[M].z;
+            const uint64_t* zp = p.ext_z ? p.ext_z + (size_t)i * p.ext_stride : (M == staged_M ? sm.zs : p.plans[M].z);
             if (built_for != i) {            // only the first instance; later ones are prefetched below
                 build_B(i, M, qb & 1);
                 fence_proxy_async_smem();
@@ -688,7 +726,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
             // normal matrix / its Cholesky factor: shared plans bring a precomputed factor; per-instance plans are
             // factored here, overlapping the epilogue of the same instance
             if (p.ext_z == nullptr) {
-                zp = p.plans[M].z; wp = p.plans[M].w;
+                zp = M == staged_M ? sm.zs : p.plans[M].z;
+                wp = M == staged_M ? sm.ws : p.plans[M].w;
                 const double* ainv = p.plans[M].ainv;        // inverse of E^T W E, computed once per plan
                 if (M != cachedM) {
                     named_bar_sync(1, WLS_THREADS);
