@@ -190,7 +190,8 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
                         ctx->G, ctx->act);
         TRY(dks::tc_launch(ctx, p));
     } else {
-        size_t smem = dks::simt_smem_bytes(S_cap, ctx->N, ctx->G);
+        const bool sfm = ctx->act == DKS_ACT_SOFTMAX;
+        size_t smem = dks::simt_smem_bytes(S_cap, ctx->N, ctx->G, sfm ? ctx->R : 1, sfm ? ctx->C : 1);
         if ((long long)smem > (long long)ctx->max_smem_optin)
             return fail(DKS_ERR_UNSUPPORTED, "SIMT kernel needs %zu B of shared memory (> %d): N*G or nsamples too large",
                         smem, ctx->max_smem_optin);
@@ -350,7 +351,8 @@ int dks_set_model(dks_ctx* ctx, const double* W_host, const double* b_host, int 
     } else if (activation == DKS_ACT_IDENTITY) {
         ctx->C = R;
     } else if (activation == DKS_ACT_SOFTMAX) {
-        return fail(DKS_ERR_UNSUPPORTED, "general softmax head (C > 2) is not implemented yet");
+        REQUIRE(R >= 2, "softmax head needs at least two score rows (got %d)", R);
+        ctx->C = R;
     } else {
         return fail(DKS_ERR_INVALID, "dks_set_model: unknown activation %d", activation);
     }
@@ -416,7 +418,8 @@ int dks_fit(dks_ctx* ctx) {
     CUDA_TRY(cudaMemcpyAsync(ctx->d_goff, ctx->h_goff.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_gcols, ctx->h_gcols.data(), sizeof(int32_t) * D, cudaMemcpyHostToDevice, st));
 
-    ctx->scale = (ctx->act == DKS_ACT_BINARY_LOGISTIC) ? -ctx->kappa * 1.4426950408889634 : 1.0;
+    ctx->scale = (ctx->act == DKS_ACT_BINARY_LOGISTIC) ? -ctx->kappa * 1.4426950408889634
+               : (ctx->act == DKS_ACT_SOFTMAX) ? 1.4426950408889634 : 1.0;
     dks::fit_bw_kernel<<<cdiv((long long)N * G * R, 256), 256, 0, st>>>(ctx->d_bg, ctx->d_W, ctx->d_goff, ctx->d_gcols, N, D,
                                                                            G, R, ctx->d_BW);
     dks::fit_scores_kernel<<<cdiv((long long)N * R, 256), 256, 0, st>>>(ctx->d_BW, ctx->d_b, N, G, R, ctx->d_scores);

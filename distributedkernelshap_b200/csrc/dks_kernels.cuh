@@ -409,25 +409,27 @@ struct SimtSmem {
     float* Bs;      // [M][N] scaled grouped background contributions of the varying groups, then bases[N], wb[N]
 };
 
-__device__ inline SimtSmem simt_carve(unsigned char* base, int S_cap) {
+__device__ inline SimtSmem simt_carve(unsigned char* base, int S_cap, int R, int ny) {
     SimtSmem s;
     s.ys = reinterpret_cast<double*>(base);
-    s.A = s.ys + S_cap;
+    s.A = s.ys + (size_t)S_cap * ny;
     s.rhs = s.A + 63 * 63;
     s.xw = s.rhs + 64;
-    s.vi = reinterpret_cast<int*>(s.xw + 64);
+    s.vi = reinterpret_cast<int*>(s.xw + 64 * (size_t)R);
     s.Bs = reinterpret_cast<float*>(s.vi + 64);
     return s;
 }
 
-__host__ __device__ inline size_t simt_smem_bytes(int S_cap, int N, int Mmax) {
-    return sizeof(double) * ((size_t)S_cap + 63 * 63 + 64 + 64) + sizeof(int) * 64 +
-           sizeof(float) * ((size_t)Mmax * N + 2 * (size_t)N);
+// ny = number of y buffers (1, or C for the softmax head), R = score rows staged per instance
+__host__ __device__ inline size_t simt_smem_bytes(int S_cap, int N, int Mmax, int R = 1, int ny = 1) {
+    return sizeof(double) * ((size_t)S_cap * ny + 63 * 63 + 64 + 64 * (size_t)R) + sizeof(int) * 64 +
+           sizeof(float) * ((size_t)Mmax * N * R + (size_t)N * R + (size_t)N);
 }
 
 __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SimtSmem sm = simt_carve(smem_raw, p.S_cap);
+    const bool softmax = p.act == DKS_ACT_SOFTMAX;
+    SimtSmem sm = simt_carve(smem_raw, p.S_cap, softmax ? p.R : 1, softmax ? p.C : 1);
     const int tid = threadIdx.x;
     const int N = p.N, G = p.G, C = p.C;
     const size_t slab = (size_t)p.n * G;
@@ -532,6 +534,75 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
                 double* phi0 = p.phi + (size_t)i * G;
                 const double* phi1 = p.phi + slab + (size_t)i * G;
                 for (int k = 0; k < M; ++k) { double v = phi1[sm.vi[k]]; phi0[sm.vi[k]] = (v == 0.0) ? 0.0 : -v; }
+            }
+        } else if (p.act == DKS_ACT_SOFTMAX) {
+            // ---- general softmax head: R = C score rows, outputs softmax(scores); scale = log2(e) ----
+            const int R = p.R;
+            float* basesR = Bs + (size_t)R * M * N;      // [R][N]
+            float* wbR = basesR + (size_t)R * N;         // [N]
+            for (int idx = tid; idx < R * M * N; idx += blockDim.x) {
+                const int r = idx / (M * N), rem = idx - r * (M * N), k = rem / N, j = rem - k * N;
+                Bs[idx] = p.BWs[((size_t)r * G + sm.vi[k]) * N + j];
+            }
+            for (int idx = tid; idx < R * N; idx += blockDim.x) basesR[idx] = p.bases[idx];
+            for (int j = tid; j < N; j += blockDim.x) wbR[j] = p.wbf[j];
+            for (int idx = tid; idx < R * M; idx += blockDim.x) {
+                const int r = idx / M, k = idx - r * M;
+                sm.xw[r * 64 + k] = p.scale * p.XW[((size_t)i * G + sm.vi[k]) * R + r];
+            }
+            __syncthreads();
+            for (int s = tid; s < S; s += blockDim.x) {
+                const uint64_t z = zp[s];
+                float af[8], acc[8];
+                for (int r = 0; r < R; ++r) {
+                    double a = 0;
+                    for (int k = 0; k < M; ++k) if ((z >> k) & 1ull) a += sm.xw[r * 64 + k];
+                    af[r] = (float)a;
+                    acc[r] = 0.f;
+                }
+                for (int j = 0; j < N; ++j) {
+                    float t[8], mx = -3.0e38f;
+                    for (int r = 0; r < R; ++r) {
+                        float c = 0.f;
+                        const float* Br = Bs + (size_t)r * M * N;
+                        for (int k = 0; k < M; ++k) if ((z >> k) & 1ull) c += Br[k * N + j];
+                        t[r] = (basesR[r * N + j] - c) + af[r];
+                        mx = fmaxf(mx, t[r]);
+                    }
+                    float den = 0.f;
+                    for (int r = 0; r < R; ++r) { t[r] = ex2_approx(t[r] - mx); den += t[r]; }
+                    const float inv = wbR[j] * rcp_approx(den);
+                    for (int r = 0; r < R; ++r) acc[r] = fmaf(t[r], inv, acc[r]);
+                }
+                for (int c = 0; c < C; ++c) {
+                    double y;
+                    if (p.link == DKS_LINK_LOGIT) {
+                        float rest = 0.f;                 // 1 - ey_c as the sum of the other classes: no cancellation
+                        for (int c2 = 0; c2 < C; ++c2) if (c2 != c) rest += acc[c2];
+                        y = log((double)acc[c] / (double)rest) - p.linkfnull[c];
+                    } else {
+                        y = (double)acc[c] - p.fnull[c];
+                    }
+                    sm.ys[(size_t)c * p.S_cap + s] = y;
+                }
+            }
+            __syncthreads();
+            if (chol != nullptr) {
+                for (int idx = tid; idx < (M - 1) * (M - 1); idx += blockDim.x) sm.A[idx] = chol[idx];
+            } else {
+                wls_build_normal(zp, wp, S, M, sm.A, threadIdx.x >> 5, blockDim.x >> 5);
+                __syncthreads();
+                if (tid < 32) {
+                    bool ok = wls_cholesky_warp(sm.A, M - 1);
+                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                }
+            }
+            for (int c = 0; c < C; ++c) {
+                __syncthreads();
+                const double delta = p.dlink[(size_t)i * C + c];
+                wls_build_rhs(zp, wp, sm.ys + (size_t)c * p.S_cap, S, M, delta, sm.rhs, threadIdx.x >> 5, blockDim.x >> 5);
+                __syncthreads();
+                if (tid == 0) wls_solve_write(sm.A, sm.rhs, M, delta, sm.vi, p.phi + (size_t)c * slab + (size_t)i * G, 1.0);
             }
         } else if (p.act == DKS_ACT_IDENTITY) {
             // identity head: the background average commutes with the head, so

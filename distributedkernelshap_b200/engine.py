@@ -20,6 +20,7 @@ from .predictors import extract_linear_spec
 logger = logging.getLogger(__name__)
 
 MODEL_CHECK_RTOL = 1e-9
+MAX_ROWS_PER_CALL = 65536     # rows per C-ABI call: bounds the engine's per-call workspace (n x S x 8 B on the fast path)
 
 
 class GpuKernelExplainer:
@@ -209,6 +210,18 @@ class GpuKernelExplainer:
         n, G = X.shape[0], self.data.groups_size
         self._set_nsamples(nsamples)
         need_hist = self._l1_guard(l1_reg, nsamples)
+
+        if n > MAX_ROWS_PER_CALL:     # large inputs go through in row chunks (results are independent per row)
+            parts = []
+            for lo in range(0, n, MAX_ROWS_PER_CALL):
+                hi = min(n, lo + MAX_ROWS_PER_CALL)
+                sub = dict(nsamples=nsamples, l1_reg=l1_reg)
+                if plans is not None:
+                    sub["plans"] = plans[lo:hi]
+                part = self.shap_values(X[lo:hi], **sub)
+                parts.append(part if isinstance(part, list) else [part])
+            merged = [np.concatenate([pt[c] for pt in parts], axis=0) for c in range(len(parts[0]))]
+            return merged if self.vector_out else merged[0]
 
         phi = np.zeros((self.D, n, G))
         if plans is not None:

@@ -330,3 +330,50 @@ def test_config2_shape_64_features_bg512():
     _compare(got, want)
     with pytest.raises(NotImplementedError):          # reference default l1_reg='auto' would select features here
         eng.shap_values(d["X_explain"], nsamples=4096)
+
+
+def test_large_input_is_chunked(monkeypatch):
+    """Inputs above MAX_ROWS_PER_CALL are explained in row chunks with identical results."""
+    from distributedkernelshap_b200 import engine as engine_mod
+    prob = make_problem(seed=13, n=700, N=20, widths=(1, 1, 2, 1, 3, 1))
+    np.random.seed(3)
+    eng = _engine(prob)
+    whole = eng.shap_values(prob["X"], nsamples=62, l1_reg=False)
+    monkeypatch.setattr(engine_mod, "MAX_ROWS_PER_CALL", 256)
+    chunked = eng.shap_values(prob["X"], nsamples=62, l1_reg=False)
+    np.testing.assert_array_equal(chunked[1], whole[1])
+    assert chunked[0].shape == (700, 6)
+
+
+@pytest.mark.parametrize("link", ["logit", "identity"])
+def test_multiclass_softmax_head(link):
+    """C = 4 multinomial logistic regression (general softmax head, CUDA-core kernel) against the oracle."""
+    from distributedkernelshap_b200.data import DenseData
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from distributedkernelshap_b200.predictors import LinearSoftmaxClassifier
+    from oracle.shap_kernel_oracle import DenseData as ODenseData, KernelExplainerOracle
+    rng = np.random.default_rng(5)
+    widths = (1, 2, 1, 3, 1, 1, 2)
+    groups, start = [], 0
+    for wd in widths:
+        groups.append(list(range(start, start + wd))); start += wd
+    D, N, n, C = start, 23, 14, 4
+    bg, X = rng.standard_normal((N, D)), rng.standard_normal((n, D))
+    clf = LinearSoftmaxClassifier(rng.normal(0, 0.8, (C, D)), rng.normal(0, 0.5, C))
+    names = [f"g{i}" for i in range(len(groups))]
+    wts = rng.uniform(0.3, 1.0, N)
+    orc = KernelExplainerOracle(clf.predict_proba, ODenseData(bg, names, groups, wts), link=link, record_plans=True)
+    eng = GpuKernelExplainer(clf.predict_proba, DenseData(bg, names, groups, wts), link=link)
+    assert eng.vector_out and eng.D == C
+    np.testing.assert_allclose(eng.expected_value, orc.expected_value, rtol=1e-12)
+    want = orc.shap_values(X, nsamples=10 ** 6, l1_reg=False)              # full enumeration (M = 7)
+    got = eng.shap_values(X, nsamples=10 ** 6, l1_reg=False)
+    assert len(got) == C
+    _compare(got, want)
+    np.random.seed(4)
+    want = orc.shap_values(X, nsamples=60, l1_reg=False)                   # sampled, per-instance plans
+    got = eng.shap_values(X, nsamples=60, l1_reg=False, plans=[(Z, w) for (_, Z, w) in orc.plans[n:]])
+    _compare(got, want)
+    fx = clf.predict_proba(X)
+    for c in range(C):
+        np.testing.assert_allclose(got[c].sum(1), orc.link.f(fx[:, c]) - eng.expected_value[c], rtol=1e-7, atol=1e-8)
