@@ -7,6 +7,7 @@
 #include "dks_kernels.cuh"
 #include "dks_tc.cuh"
 #include "dks_shared.cuh"
+#include "dks_sampler.cuh"
 
 namespace {
 
@@ -107,6 +108,32 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     REQUIRE(ctx->prepared, "dks_explain: call dks_prepare_* first");
     REQUIRE((ext_z == nullptr) == (ext_w == nullptr), "ext_zbits and ext_w must both be given or both be NULL");
     const int n = ctx->cur_n;
+    if (ctx->plan_mode == 1 && ext_z == nullptr) {
+        // every instance draws its own plan on the device; the explain kernels then read it like a caller-supplied one
+        if (ctx->max_plan_S < 2)
+            return fail(DKS_ERR_PLAN_MISSING, "per-instance plans need the shared plans of the M values present (their "
+                        "enumerated prefix); none is set");
+        const int stride = (ctx->max_plan_S + 1) & ~1;
+        const size_t need = (size_t)n * stride;
+        if (need > ctx->cap_gen) {
+            TRY(dev_alloc(&ctx->d_genz, need)); TRY(dev_alloc(&ctx->d_genw, need));
+            ctx->cap_gen = need;
+        }
+        if (!ctx->d_sinfo) TRY(dev_alloc(&ctx->d_sinfo, (size_t)(DKS_MAX_GROUPS + 1)));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_sinfo, ctx->h_sinfo, sizeof(ctx->h_sinfo), cudaMemcpyHostToDevice, ctx->stream));
+        dks::sampler::SamplerParams sp;
+        sp.n = n; sp.G = ctx->G; sp.S_req = ctx->nsamples_req; sp.stride = stride; sp.seed = ctx->sampler_seed;
+        sp.row_offset = ctx->row_offset; sp.Mcnt = ctx->d_M; sp.plans = ctx->d_plans; sp.info = ctx->d_sinfo;
+        sp.out_z = ctx->d_genz; sp.out_w = ctx->d_genw; sp.status = ctx->d_status;
+        const size_t ssm = dks::sampler::smem_bytes();
+        CUDA_TRY(cudaFuncSetAttribute(dks::sampler::sample_plans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+        const int sgrid = n < ctx->sm_count ? n : ctx->sm_count;
+        dks::sampler::sample_plans_kernel<<<sgrid, dks::sampler::THREADS, ssm, ctx->stream>>>(sp);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        ctx->gen_stride = stride; ctx->gen_n = n;
+        ext_z = ctx->d_genz; ext_w = ctx->d_genw; ext_stride = stride;
+    }
     ExplainParams p;
     memset(&p, 0, sizeof(p));
     p.n = n; p.N = ctx->N; p.G = ctx->G; p.R = ctx->R; p.C = ctx->C;
@@ -278,7 +305,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums);
-    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
@@ -574,6 +601,44 @@ int dks_clear_plans(dks_ctx* ctx) {
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present) {
     REQUIRE(ctx && present && M >= 0 && M <= DKS_MAX_GROUPS, "dks_has_shared_plan: bad arguments");
     *present = (ctx->h_plans[M].z != nullptr && ctx->h_plans[M].S == dks_effective_S(M, ctx->nsamples_req)) ? 1 : 0;
+    return DKS_OK;
+}
+
+int dks_set_plan_sampling(dks_ctx* ctx, int M, int nfixed, int n_full, int n_paired, int ncdf, const double* cdf_host,
+                          double weight_left) {
+    REQUIRE(ctx && M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_plan_sampling: M out of range");
+    REQUIRE(ncdf >= 0 && ncdf <= 32 && (ncdf == 0 || cdf_host), "dks_set_plan_sampling: at most 32 sampled subset sizes");
+    REQUIRE(nfixed >= 0 && n_full >= 0 && n_paired >= 0, "dks_set_plan_sampling: bad arguments");
+    DksSamplingInfo& inf = ctx->h_sinfo[M];
+    memset(&inf, 0, sizeof(inf));
+    inf.nfixed = nfixed; inf.n_full = n_full; inf.n_paired = n_paired; inf.ncdf = ncdf; inf.weight_left = weight_left;
+    for (int k = 0; k < ncdf; ++k) inf.cdf[k] = cdf_host[k];
+    return DKS_OK;
+}
+
+int dks_set_plan_mode(dks_ctx* ctx, int mode, uint64_t seed) {
+    REQUIRE(ctx && (mode == 0 || mode == 1), "dks_set_plan_mode: mode must be 0 (shared per M) or 1 (per instance, device-drawn)");
+    ctx->plan_mode = mode;
+    ctx->sampler_seed = seed;
+    return DKS_OK;
+}
+
+int dks_set_row_offset(dks_ctx* ctx, int64_t offset) {
+    REQUIRE(ctx && offset >= 0, "dks_set_row_offset: bad arguments");
+    ctx->row_offset = (long long)offset;
+    return DKS_OK;
+}
+
+int dks_get_instance_plans(dks_ctx* ctx, uint64_t* zbits_host, double* w_host, int* n_out, int* stride_out) {
+    BIND(ctx);
+    REQUIRE(n_out && stride_out, "dks_get_instance_plans: bad arguments");
+    *n_out = ctx->gen_n; *stride_out = ctx->gen_stride;
+    if (zbits_host && w_host && ctx->gen_n > 0) {
+        const size_t cnt = (size_t)ctx->gen_n * ctx->gen_stride;
+        CUDA_TRY(cudaMemcpyAsync(zbits_host, ctx->d_genz, sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(w_host, ctx->d_genw, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     return DKS_OK;
 }
 

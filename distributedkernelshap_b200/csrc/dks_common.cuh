@@ -24,6 +24,16 @@ struct PlanDev {
     int S_pad;
 };
 
+// What the device-side sampler needs to continue a plan past its enumerated prefix (per M; plan.py: sampling_info)
+struct DksSamplingInfo {
+    int nfixed;           // enumerated rows
+    int n_full;           // fully enumerated subset sizes
+    int n_paired;         // sizes whose complement has a different size
+    int ncdf;             // sizes left to sample (0: the plan is fully enumerated)
+    double weight_left;   // kernel mass of the sampled sizes
+    double cdf[32];       // cumulative probabilities of the sampled sizes (last = 1)
+};
+
 // nsamples resolution of KernelExplainer.explain: 'auto' (req <= 0) = 2M + 2^11; capped at 2^M - 2 for M <= 30
 __host__ __device__ __forceinline__ int dks_effective_S(int M, int req) {
     long long s = req > 0 ? (long long)req : 2LL * M + 2048;
@@ -104,6 +114,16 @@ struct dks_ctx {
     PlanDev* d_plans = nullptr;
     std::vector<void*> plan_allocs;
     int max_plan_S = 0;
+    // per-instance plans drawn on the device (plan_mode 1)
+    int plan_mode = 0;
+    uint64_t sampler_seed = 0;
+    long long row_offset = 0;
+    DksSamplingInfo h_sinfo[DKS_MAX_GROUPS + 1];
+    DksSamplingInfo* d_sinfo = nullptr;
+    uint64_t* d_genz = nullptr;
+    double* d_genw = nullptr;
+    size_t cap_gen = 0;
+    int gen_stride = 0, gen_n = 0;
 
     // per-call workspace
     int cap_n = 0, cur_n = 0;

@@ -459,13 +459,13 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
         } else {
             PlanDev pd = p.plans[M];
             if (pd.z == nullptr || pd.S != S) {
-                if (tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING); p.status[1] = M; }
+                if (tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING) == 0) p.status[1] = M; }
                 continue;
             }
             zp = pd.z; wp = pd.w; chol = pd.chol;
         }
         if (S > p.S_cap) {
-            if (tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_INVALID); p.status[1] = i; }
+            if (tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_INVALID) == 0) p.status[1] = i; }
             continue;
         }
 
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
                 __syncthreads();
                 if (tid < 32) {
                     bool ok = wls_cholesky_warp(sm.A, M - 1);
-                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                    if (!ok && tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
                 }
             }
             Lf = sm.A;
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
                 __syncthreads();
                 if (tid < 32) {
                     bool ok = wls_cholesky_warp(sm.A, M - 1);
-                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                    if (!ok && tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
                 }
             }
             for (int c = 0; c < C; ++c) {
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
                 __syncthreads();
                 if (tid < 32) {
                     bool ok = wls_cholesky_warp(sm.A, M - 1);
-                    if (!ok && tid == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                    if (!ok && tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
                 }
             }
             Lf = sm.A;

@@ -714,8 +714,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 } else if (M >= 2 && wtid == 0) {
                     int S0 = dks_effective_S(M, p.S_req);
                     bool missing = p.ext_z == nullptr && (p.plans[M].z == nullptr || p.plans[M].S != S0);
-                    if (missing) { atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING); p.status[1] = M; }
-                    else { atomicCAS(&p.status[0], 0, DKS_ERR_INVALID); p.status[1] = i; }
+                    if (missing) { if (atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING) == 0) p.status[1] = M; }
+                    else { if (atomicCAS(&p.status[0], 0, DKS_ERR_INVALID) == 0) p.status[1] = i; }
                 }
                 mbar_arrive_warp(&inst_empty[q & 1]);
                 continue;
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 named_bar_sync(1, WLS_THREADS);
                 if (ww == 0) {
                     bool ok = wls_cholesky_warp(sm.chol, nA);
-                    if (!ok && lane == 0) { atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC); p.status[1] = i; }
+                    if (!ok && lane == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
                 }
             }
             const double delta = p.dlink[(size_t)i * C + 1];

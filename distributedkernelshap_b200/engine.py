@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _cabi
 from .data import DenseData, convert_to_data, convert_to_link
-from .plan import build_plan, pack_dense_plan, resolve_nsamples
+from .plan import build_plan, pack_dense_plan, resolve_nsamples, sampling_info
 from .predictors import extract_linear_spec
 
 logger = logging.getLogger(__name__)
@@ -42,11 +42,15 @@ class GpuKernelExplainer:
         CUDA device ordinal (default: ``LOCAL_RANK`` under torchrun, else 0).
     """
 
-    def __init__(self, model, data, link="identity", seed=None, device=None, kernel="auto", **kwargs):
+    def __init__(self, model, data, link="identity", seed=None, device=None, kernel="auto", plan_mode="shared", **kwargs):
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        if plan_mode not in ("shared", "per_instance"):
+            raise ValueError("plan_mode must be 'shared' or 'per_instance'")
         if seed is not None:
             np.random.seed(seed)
+        self.plan_mode = plan_mode
+        self.plan_seed = 0 if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self.lib = _cabi.load()
         self.link = convert_to_link(link)
         self.model_callable = model
@@ -82,6 +86,7 @@ class GpuKernelExplainer:
         link_code = _cabi.LINK_LOGIT if str(self.link) == "logit" else _cabi.LINK_IDENTITY
         _cabi.check(self.lib.dks_set_link(self._ctx, link_code))
         self.set_kernel(kernel)
+        _cabi.check(self.lib.dks_set_plan_mode(self._ctx, 1 if plan_mode == "per_instance" else 0, self.plan_seed))
         _cabi.check(self.lib.dks_fit(self._ctx))
 
         self.D = self.spec.n_outputs
@@ -159,6 +164,13 @@ class GpuKernelExplainer:
                 continue
             plan = build_plan(M, nsamples)  # draws from the global legacy stream, like the reference
             _cabi.check(self.lib.dks_set_shared_plan(self._ctx, M, plan.S, _cabi.ptr(plan.zbits), _cabi.ptr(plan.weights)))
+            nfixed, n_full, n_paired, cdf, weight_left = sampling_info(plan)
+            if len(cdf) > 32:
+                if self.plan_mode == "per_instance":
+                    raise NotImplementedError(f"per-instance device plans support at most 32 sampled subset sizes (M={M})")
+                continue
+            _cabi.check(self.lib.dks_set_plan_sampling(self._ctx, M, nfixed, n_full, n_paired, len(cdf),
+                                                       _cabi.ptr(cdf) if len(cdf) else None, weight_left))
 
     def m_histogram(self):
         hist = np.zeros(self.data.groups_size + 1, dtype=np.int32)
@@ -184,6 +196,7 @@ class GpuKernelExplainer:
         nsamples = kwargs.pop("nsamples", "auto")
         l1_reg = kwargs.pop("l1_reg", "auto")
         plans = kwargs.pop("plans", None)
+        row_offset = int(kwargs.pop("row_offset", 0))
         kwargs.pop("silent", None)
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
@@ -215,7 +228,7 @@ class GpuKernelExplainer:
             parts = []
             for lo in range(0, n, MAX_ROWS_PER_CALL):
                 hi = min(n, lo + MAX_ROWS_PER_CALL)
-                sub = dict(nsamples=nsamples, l1_reg=l1_reg)
+                sub = dict(nsamples=nsamples, l1_reg=l1_reg, row_offset=row_offset + lo)
                 if plans is not None:
                     sub["plans"] = plans[lo:hi]
                 part = self.shap_values(X[lo:hi], **sub)
@@ -224,6 +237,9 @@ class GpuKernelExplainer:
             return merged if self.vector_out else merged[0]
 
         phi = np.zeros((self.D, n, G))
+        if self.plan_mode == "per_instance":
+            # the device draws each row's plan from (seed, global row index): tell it where this block starts
+            _cabi.check(self.lib.dks_set_row_offset(self._ctx, row_offset))
         if plans is not None:
             zb, w, stride = self._pack_external_plans(plans, n, nsamples)
             if need_hist:
@@ -249,6 +265,17 @@ class GpuKernelExplainer:
         if single:
             return [phi[c, 0] for c in range(self.D)]
         return [phi[c] for c in range(self.D)]
+
+    def instance_plans(self):
+        """Plans the device drew in the last ``plan_mode='per_instance'`` call: ``(zbits uint64[n, stride],
+        w float64[n, stride])`` -- rows past an instance's S are zero.  For audits and tests."""
+        n, stride = C.c_int(0), C.c_int(0)
+        _cabi.check(self.lib.dks_get_instance_plans(self._ctx, None, None, C.byref(n), C.byref(stride)))
+        zb = np.zeros((n.value, stride.value), dtype=np.uint64)
+        w = np.zeros((n.value, stride.value), dtype=np.float64)
+        if n.value:
+            _cabi.check(self.lib.dks_get_instance_plans(self._ctx, _cabi.ptr(zb), _cabi.ptr(w), C.byref(n), C.byref(stride)))
+        return zb, w
 
     def _pack_external_plans(self, plans, n, nsamples):
         if len(plans) != n:

@@ -21,6 +21,7 @@ from functools import partial
 from typing import Any, Callable, Dict, List, Optional, Union
 
 import numpy as np
+from scipy import sparse
 
 from distributedkernelshap_b200 import parallel
 from distributedkernelshap_b200.explainers.utils import batch, batch_slices
@@ -94,14 +95,23 @@ class DistributedExplainer:
                 for k in range(n_workers)]
 
     def get_explanation(self, X: np.ndarray, **kwargs) -> np.ndarray:
-        """Explains the rows of ``X`` in parallel; ``kwargs`` go to the explainer's ``shap_values``."""
-        target_fn = partial(self.target_fn, kwargs=kwargs) if kwargs is not None else self.target_fn
+        """Explains the rows of ``X`` in parallel; ``kwargs`` go to the explainer's ``shap_values``.  Every mini-batch
+        is sent with the index of its first row (``row_offset``) so that device-drawn per-instance plans depend on the
+        row, not on how the rows were split over workers."""
+        kwargs = dict(kwargs or {})
         if self.spmd:
-            return self._get_explanation_spmd(X, target_fn)
+            return self._get_explanation_spmd(X, kwargs)
 
-        batched_instances = batch(X, batch_size=self.batch_size, n_batches=self.n_jobs)
+        if sparse.issparse(X):
+            X = X.toarray()
+        slices = batch_slices(X.shape[0], self.batch_size, self.n_jobs)
+        items = [((idx, X[sl]), sl.start) for idx, sl in enumerate(slices)]
+
+        def call(actor, item, start):
+            return self.target_fn(actor, item, kwargs={**kwargs, "row_offset": start})
+
         if len(self.pool) == 1:
-            unordered = [target_fn(self.pool[0], item) for item in enumerate(batched_instances)]
+            unordered = [call(self.pool[0], item, start) for item, start in items]
             return self.order_result(unordered)
 
         # ActorPool.map_unordered: a free worker takes the next mini-batch
@@ -110,33 +120,36 @@ class DistributedExplainer:
         for actor in self.pool:
             free.put(actor)
 
-        def run(item):
+        def run(item, start):
             actor = free.get()
             try:
-                return target_fn(actor, item)
+                return call(actor, item, start)
             finally:
                 free.put(actor)
 
         with ThreadPoolExecutor(max_workers=len(self.pool)) as ex:
-            futures = [ex.submit(run, item) for item in enumerate(batched_instances)]
+            futures = [ex.submit(run, item, start) for item, start in items]
             unordered = [f.result() for f in as_completed(futures)]
         return self.order_result(unordered)
 
-    def _get_explanation_spmd(self, X, target_fn):
+    def _get_explanation_spmd(self, X, kwargs):
         """One process per GPU: explain this rank's row block, then all-gather the shap values."""
         rank, world = parallel.rank(), parallel.world_size()
+        if sparse.issparse(X):
+            X = X.toarray()
         n = X.shape[0]
         blocks = batch_slices(n, None, world)          # np.array_split rule
         counts = [b.stop - b.start for b in blocks]
         mine = X[blocks[rank]]
         if mine.shape[0] > 0:
-            local_batches = batch(mine, batch_size=self.batch_size, n_batches=1)
-            results = [target_fn(self.pool[0], item) for item in enumerate(local_batches)]
+            local_slices = batch_slices(mine.shape[0], self.batch_size, 1)
+            results = [self.target_fn(self.pool[0], (idx, mine[sl]),
+                                      kwargs={**kwargs, "row_offset": blocks[rank].start + sl.start})
+                       for idx, sl in enumerate(local_slices)]
             local = self.order_result(results)
         else:
             local = None
         vector_out = self.pool[0].return_attribute("vector_out")
-        n_out = len(local) if isinstance(local, list) else 1
         G = self.pool[0].return_attribute("data").groups_size
         if local is None:
             stacked = np.zeros((self.pool[0].return_attribute("D"), 0, G))

@@ -118,13 +118,18 @@ class KernelShap(Explainer, FitMixin):
                  categorical_names: Optional[Dict[int, List[str]]] = None,
                  task: str = 'classification',
                  seed: int = None,
-                 distributed_opts: Optional[Dict] = None):
+                 distributed_opts: Optional[Dict] = None,
+                 plan_mode: str = 'shared'):
         """KernelSHAP explainer with grouping of encoded categorical variables; see the reference docstring
         (kernel_shap.py:274-337) for parameter semantics -- they are unchanged.
 
         ``distributed_opts``: ``n_cpus`` now counts worker GPUs (one CUDA context each) instead of ray CPU actors,
         ``batch_size`` still sets the mini-batch of rows sent to a worker at a time.  Under ``torchrun`` every rank is
-        one worker and the shap values are all-gathered over NCCL."""
+        one worker and the shap values are all-gathered over NCCL.
+
+        ``plan_mode`` (not in the reference): ``'shared'`` evaluates one coalition plan per number of varying groups for
+        all instances (drawn on the host from the seeded NumPy stream); ``'per_instance'`` draws a fresh plan for every
+        instance on the GPU, as shap does on the CPU, from a counter-based stream keyed by (seed, row index)."""
         super().__init__(meta=copy.deepcopy(DEFAULT_META_KERNEL_SHAP))
 
         self.link = link
@@ -133,6 +138,7 @@ class KernelShap(Explainer, FitMixin):
         self.categorical_names = categorical_names if categorical_names else {}
         self.task = task
         self.seed = seed
+        self.plan_mode = plan_mode
         self._update_metadata({"task": self.task})
 
         self.use_groups = False            # user passed groups / group names
@@ -364,6 +370,8 @@ class KernelShap(Explainer, FitMixin):
         self.background_data = self._get_data(background_data, group_names, groups, weights, **kwargs)
         explainer_args = (self.predictor, self.background_data)
         explainer_kwargs = {'link': self.link}
+        if self.plan_mode != 'shared':
+            explainer_kwargs.update(plan_mode=self.plan_mode, seed=self.seed)
         if self.distribute:
             explainer_kwargs['seed'] = self.seed  # every worker seeds its own stream
             self._explainer = DistributedExplainer(

@@ -157,6 +157,24 @@ def build_plan(M, nsamples="auto", rng=None):
     return CoalitionPlan(M, zbits, weights, nfixed, n_full, weight_left)
 
 
+def sampling_info(plan):
+    """What the device-side sampler (csrc/dks_sampler.cuh, ``dks_set_plan_sampling``) needs to continue a plan past its
+    enumerated prefix: ``(nfixed, n_full, n_paired, cdf float64[ncdf], weight_left)``.  ``cdf`` is the cumulative
+    distribution of the subset sizes left to sample -- upstream's ``remaining_weight_vector`` after halving the paired
+    sizes and renormalising -- and is empty when the plan is fully enumerated."""
+    wv, n_sizes, n_paired = size_weights(plan.M)
+    n_full = plan.num_full_subsets
+    if n_full == n_sizes:
+        return plan.nfixed, n_full, n_paired, np.zeros(0), 0.0
+    p = wv.copy()
+    p[:n_paired] /= 2
+    p = p[n_full:]
+    p /= p.sum()
+    cdf = np.cumsum(p)
+    cdf[-1] = 1.0
+    return plan.nfixed, n_full, n_paired, np.ascontiguousarray(cdf), float(wv[n_full:].sum())
+
+
 def pack_dense_plan(Z):
     """[S, M] 0/1 matrix -> uint64[S] bit words (for feeding externally built plans to the engine)."""
     Z = np.asarray(Z)

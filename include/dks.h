@@ -97,6 +97,20 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
 int dks_clear_plans(dks_ctx* ctx);
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present);
 
+/* ---- per-instance plans drawn on the device -----------------------------------------------------------
+ * shap.KernelExplainer.explain draws a fresh plan for every instance (the sampling loop that follows the subset
+ * enumeration; reached from kernel_shap.py:250/253).  Mode 1 does that on the GPU: the enumerated prefix comes from the
+ * shared plan of the instance's M, the sampled rows from Philox4x32-10 keyed by `seed` with counter (draw, global row),
+ * with upstream's duplicate / complement / truncation / rescaling rules.  Plans depend on the global row index only
+ * (dks_set_row_offset gives the index of row 0 of the next call), never on batching or the number of GPUs.
+ * dks_set_plan_sampling uploads what the sampler needs for one M (plan.py: sampling_info); cdf has ncdf <= 32 entries. */
+int dks_set_plan_sampling(dks_ctx* ctx, int M, int nfixed, int n_full, int n_paired, int ncdf, const double* cdf_host,
+                          double weight_left);
+int dks_set_plan_mode(dks_ctx* ctx, int mode /* 0 shared per M, 1 per instance */, uint64_t seed);
+int dks_set_row_offset(dks_ctx* ctx, int64_t offset);
+/* plans of the last mode-1 explain call ([n][stride] each; pass NULL buffers to query n and stride); tests / audit. */
+int dks_get_instance_plans(dks_ctx* ctx, uint64_t* zbits_host, double* w_host, int* n_out, int* stride_out);
+
 /* ---- explain: KernelExplainer.shap_values (reached from kernel_shap.py:250/253) ---------------------
  * Stage 1 (dks_prepare_*): per instance, grouped contributions W_g x_g, f(x), link(f(x)) - link(fnull),
  * varying_groups() bit-mask and M.  X is [n x D] row-major float64. */

@@ -38,3 +38,28 @@ def test_plan_rejects_unsupported_sizes():
         build_plan(1)
     with pytest.raises(ValueError):
         build_plan(65)
+
+
+def test_sampling_info_and_philox_stream_adapter():
+    """sampling_info() describes the sampled part of a plan, and the Philox stream adapter used to check the device
+    sampler drives the product's and the oracle's plan builders to the same plan."""
+    from oracle.shap_kernel_oracle import build_plan as oracle_build_plan
+    from sampler_twin import PhiloxPlanStream, philox4x32_10
+    from distributedkernelshap_b200.plan import build_plan, pack_dense_plan, sampling_info
+    # Philox4x32-10 known-answer vectors (Random123 kat_vectors)
+    assert philox4x32_10((0, 0), (0, 0, 0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert philox4x32_10((0xffffffff, 0xffffffff), (0xffffffff,) * 4) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox4x32_10((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    for M, ns in [(12, 300), (6, 40), (9, 120), (20, "auto")]:
+        plan = build_plan(M, ns, rng=PhiloxPlanStream(123, 7))
+        Z, w, info = oracle_build_plan(M, plan.S, rng=PhiloxPlanStream(123, 7))
+        np.testing.assert_array_equal(plan.zbits, pack_dense_plan(Z))
+        np.testing.assert_allclose(plan.weights, w, rtol=1e-14)
+        nfixed, n_full, n_paired, cdf, weight_left = sampling_info(plan)
+        assert nfixed == info["nfixed"] and n_full == info["num_full_subsets"]
+        assert n_paired == info["num_paired_subset_sizes"]
+        assert len(cdf) == info["num_subset_sizes"] - n_full and cdf[-1] == 1.0 and np.all(np.diff(cdf) > 0)
+        assert abs(weight_left - info["weight_left"]) < 1e-15
+    full = build_plan(5, 1000)
+    assert len(sampling_info(full)[3]) == 0
