@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05", "shared"])
+    ap.add_argument("--plan-mode", default="shared", choices=["shared", "per_instance"],
+                    help="shared: one coalition plan per M for all instances (default, the headline); per_instance: a fresh "
+                         "plan per instance drawn on the GPU (what shap does on the CPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-oracle timing")
     ap.add_argument("--cpu-sample", type=int, default=16, help="instances the CPU baseline explains")
     return ap.parse_args()
@@ -54,11 +57,12 @@ def workload(rank=0):
     return base
 
 
-def config_dict(world, kernel):
+def config_dict(world, kernel, plan_mode="shared"):
     return {"workload": "Adult-shaped synthetic LR (BASELINE.json configs[1]): 2560 instances/GPU, D=49, 12 groups, "
                         "bg=100, nsamples=2048, l1_reg=False, logit link",
             "instances_per_gpu": N_INSTANCES, "global_instances": N_INSTANCES * world, "background": N_BACKGROUND,
-            "nsamples": NSAMPLES, "features": 49, "groups": 12, "plan": "shared per M (seed 0)",
+            "nsamples": NSAMPLES, "features": 49, "groups": 12,
+            "plan": "shared per M (seed 0)" if plan_mode == "shared" else "per instance, drawn on the GPU (Philox, seed 0)",
             "parallelism": f"dp{world} (instances sharded, one all-gather of phi)", "kernel": kernel,
             "l2_flush_between_steps": True}
 
@@ -201,7 +205,7 @@ def run_ours(args):
     # the reference's call sequence (benchmarks/ray_pool.py:34-37); under torchrun distributed_opts selects the SPMD path
     dopts = {"n_cpus": world, "batch_size": None, "actor_cpu_fraction": 1.0} if world > 1 else None
     explainer = KernelShap(wl["predictor"].predict_proba, link="logit", feature_names=wl["group_names"], seed=0,
-                           distributed_opts=dopts)
+                           distributed_opts=dopts, plan_mode=args.plan_mode)
     explainer.fit(wl["data"]["background"]["X"]["preprocessed"], group_names=wl["group_names"], groups=wl["groups"])
     plugin = explainer._explainer                       # DistributedExplainer (N > 1) or the engine itself
     engine = plugin.pool[0] if world > 1 else plugin
@@ -308,9 +312,11 @@ def run_ours(args):
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     mufu_peak = 148 * 16 * sm_mhz * 1e6                          # MUFU ops/s at the observed clock (16 lanes/clk/SM, measured)
     kname, mufu_per_elem = {
-        "auto": ("explain_shared_kernel + wls_shared_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
-        "shared": ("explain_shared_kernel + wls_shared_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
+        "auto": ("explain_shared_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
+        "shared": ("explain_shared_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
         "tcgen05": ("explain_tcgen05_kernel", 1.5), "simt": ("explain_simt_kernel", 2.0)}[engine.kernel]
+    if args.plan_mode == "per_instance" and engine.kernel != "simt":
+        kname, mufu_per_elem = "sample_plans_kernel + explain_tcgen05_kernel (per-instance plans)", 1.5
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kname, "kernel_ms": k_ms, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes of the reference-shaped masked batch (4*S*N*D per instance, SURVEY "
@@ -322,7 +328,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 sigmoid/accumulate, f64 link + WLS", "data": "synthetic",
-            "config": config_dict(world, engine.kernel),
+            "config": config_dict(world, engine.kernel, args.plan_mode),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -108,6 +108,9 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     REQUIRE(ctx->prepared, "dks_explain: call dks_prepare_* first");
     REQUIRE((ext_z == nullptr) == (ext_w == nullptr), "ext_zbits and ext_w must both be given or both be NULL");
     const int n = ctx->cur_n;
+    const double* ext_chol = nullptr;
+    const double* ext_ainv = nullptr;
+    int ext_fstride = 0;
     if (ctx->plan_mode == 1 && ext_z == nullptr) {
         // every instance draws its own plan on the device; the explain kernels then read it like a caller-supplied one
         if (ctx->max_plan_S < 2)
@@ -119,20 +122,51 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             TRY(dev_alloc(&ctx->d_genz, need)); TRY(dev_alloc(&ctx->d_genw, need));
             ctx->cap_gen = need;
         }
+        const int nAmax = ctx->G > 1 ? ctx->G - 1 : 1;
+        const int fstride = nAmax * nAmax;
+        const size_t needf = (size_t)n * fstride;
+        if (needf > ctx->cap_genf) {
+            TRY(dev_alloc(&ctx->d_genchol, needf)); TRY(dev_alloc(&ctx->d_genainv, needf));
+            ctx->cap_genf = needf;
+        }
         if (!ctx->d_sinfo) TRY(dev_alloc(&ctx->d_sinfo, (size_t)(DKS_MAX_GROUPS + 1)));
+        if (!ctx->d_afix) TRY(dev_alloc(&ctx->d_afix, (size_t)(DKS_MAX_GROUPS + 1)));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_sinfo, ctx->h_sinfo, sizeof(ctx->h_sinfo), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_afix, ctx->h_afix, sizeof(ctx->h_afix), cudaMemcpyHostToDevice, ctx->stream));
+        // table sized for the largest sampled part among the plans set (a plan's sampled rows <= its S)
+        int max_left = 32;
+        for (int M = 2; M <= ctx->G && M <= DKS_MAX_GROUPS; ++M)
+            if (ctx->h_plans[M].z && ctx->h_sinfo[M].ncdf > 0) {
+                const int left = ctx->h_plans[M].S - ctx->h_sinfo[M].nfixed;
+                if (left > max_left) max_left = left;
+            }
+        max_left = (max_left + 31) / 32 * 32;
+        if (max_left > dks::sampler::MAX_SAMPLED)
+            return fail(DKS_ERR_UNSUPPORTED, "per-instance plans: %d sampled rows per plan exceed the sampler's limit of %d",
+                        max_left, dks::sampler::MAX_SAMPLED);
+        int cap = 256;
+        while (cap < 2 * max_left) cap <<= 1;
         dks::sampler::SamplerParams sp;
         sp.n = n; sp.G = ctx->G; sp.S_req = ctx->nsamples_req; sp.stride = stride; sp.seed = ctx->sampler_seed;
+        sp.table_cap = cap; sp.max_left = max_left; sp.fstride = fstride;
         sp.row_offset = ctx->row_offset; sp.Mcnt = ctx->d_M; sp.plans = ctx->d_plans; sp.info = ctx->d_sinfo;
-        sp.out_z = ctx->d_genz; sp.out_w = ctx->d_genw; sp.status = ctx->d_status;
-        const size_t ssm = dks::sampler::smem_bytes();
+        sp.afix = ctx->d_afix;
+        sp.out_z = ctx->d_genz; sp.out_w = ctx->d_genw; sp.out_chol = ctx->d_genchol; sp.out_ainv = ctx->d_genainv;
+        sp.status = ctx->d_status;
+        const size_t ssm = dks::sampler::smem_bytes(cap, max_left, ctx->G);
+        if (ssm + 2048 > (size_t)ctx->max_smem_optin)
+            return fail(DKS_ERR_UNSUPPORTED, "per-instance plan sampler needs %zu B of shared memory", ssm);
         CUDA_TRY(cudaFuncSetAttribute(dks::sampler::sample_plans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-        const int sgrid = n < ctx->sm_count ? n : ctx->sm_count;
+        int per_sm = (int)((size_t)ctx->max_smem_optin / (ssm + 2048));
+        if (per_sm > 6) per_sm = 6;
+        if (per_sm < 1) per_sm = 1;
+        const int sgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;
         dks::sampler::sample_plans_kernel<<<sgrid, dks::sampler::THREADS, ssm, ctx->stream>>>(sp);
         ctx->launches += 1;
         CUDA_TRY(cudaGetLastError());
         ctx->gen_stride = stride; ctx->gen_n = n;
         ext_z = ctx->d_genz; ext_w = ctx->d_genw; ext_stride = stride;
+        ext_chol = ctx->d_genchol; ext_ainv = ctx->d_genainv; ext_fstride = fstride;
     }
     ExplainParams p;
     memset(&p, 0, sizeof(p));
@@ -143,6 +177,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     p.fnull = ctx->d_fnull; p.linkfnull = ctx->d_linkfnull;
     p.XW = ctx->d_XW; p.vmask = ctx->d_vmask; p.Mcnt = ctx->d_M; p.dlink = ctx->d_dlink;
     p.plans = ctx->d_plans; p.ext_z = ext_z; p.ext_w = ext_w; p.ext_stride = ext_stride;
+    p.ext_chol = ext_chol; p.ext_ainv = ext_ainv; p.ext_fstride = ext_fstride;
     p.phi = phi_dev; p.status = ctx->d_status;
     // capacity of the per-CTA y buffer: the largest S any instance can need
     int S_cap = 0;
@@ -305,7 +340,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums);
-    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
@@ -580,6 +615,8 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         }
     }
     ctx->h_plans[M] = pd;
+    ctx->h_afix[M] = nullptr;                       // sampling info of a replaced plan is stale
+    memset(&ctx->h_sinfo[M], 0, sizeof(ctx->h_sinfo[M]));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (S > ctx->max_plan_S) ctx->max_plan_S = S;
@@ -593,6 +630,8 @@ int dks_clear_plans(dks_ctx* ctx) {
     for (void* p : ctx->plan_allocs) cudaFree(p);
     ctx->plan_allocs.clear();
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+    memset(ctx->h_afix, 0, sizeof(ctx->h_afix));
+    memset(ctx->h_sinfo, 0, sizeof(ctx->h_sinfo));
     ctx->max_plan_S = 0;
     CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
     return DKS_OK;
@@ -613,6 +652,17 @@ int dks_set_plan_sampling(dks_ctx* ctx, int M, int nfixed, int n_full, int n_pai
     memset(&inf, 0, sizeof(inf));
     inf.nfixed = nfixed; inf.n_full = n_full; inf.n_paired = n_paired; inf.ncdf = ncdf; inf.weight_left = weight_left;
     for (int k = 0; k < ncdf; ++k) inf.cdf[k] = cdf_host[k];
+    // normal matrix of the enumerated prefix: the per-instance sampler adds the sampled rows' part to it
+    const PlanDev& pd = ctx->h_plans[M];
+    REQUIRE(pd.z != nullptr && nfixed <= pd.S, "dks_set_plan_sampling: set the shared plan of M=%d first", M);
+    BIND(ctx);
+    double* af = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&af, sizeof(double) * (M - 1) * (M - 1)));
+    ctx->plan_allocs.push_back(af);
+    dks::plan_prefix_normal_kernel<<<1, 256, sizeof(double) * (M - 1) * (M - 1), ctx->stream>>>(pd.z, pd.w, nfixed, M, af);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    ctx->h_afix[M] = af;
     return DKS_OK;
 }
 

@@ -66,6 +66,9 @@ struct ExplainParams {
     const uint64_t* ext_z;  // per-instance plans or NULL
     const double* ext_w;
     int ext_stride;
+    const double* ext_chol;   // per-instance Cholesky factor / inverse of E^T W E prepared with the plans ([n][ext_fstride],
+    const double* ext_ainv;   // compact (M-1) x (M-1) row-major), or NULL: the explain kernel builds and factors it
+    int ext_fstride;
     double* phi;          // [C][n][G]
     int* status;          // [2] {code, detail}
     const int* list;      // instances this launch handles (NULL = all n) ...
@@ -122,7 +125,11 @@ struct dks_ctx {
     DksSamplingInfo* d_sinfo = nullptr;
     uint64_t* d_genz = nullptr;
     double* d_genw = nullptr;
-    size_t cap_gen = 0;
+    double* d_genchol = nullptr;
+    double* d_genainv = nullptr;
+    size_t cap_gen = 0, cap_genf = 0;
+    const double* h_afix[DKS_MAX_GROUPS + 1] = {};   // per M: normal matrix of the enumerated prefix (device pointers)
+    const double** d_afix = nullptr;
     int gen_stride = 0, gen_n = 0;
 
     // per-call workspace

@@ -364,20 +364,19 @@ __device__ inline void wls_solve_write(const double* Lf, double* rhs, int M, dou
     phi_row[vi[nA]] = sign * last;
 }
 
-// factor the normal matrix of a shared plan once (dks_set_shared_plan): one CTA
-__global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int S, int M,
-                                   double* __restrict__ chol, double* __restrict__ ainv, int* __restrict__ status) {
-    extern __shared__ double sm_d[];
-    double* A = sm_d;
-    const int nA = M - 1;
-    wls_build_normal(z, w, S, M, A, threadIdx.x >> 5, blockDim.x >> 5);
+// Block-level: Cholesky factor and inverse of the nA x nA matrix in A (shared memory, row-major; A must be followed by
+// nA*nA doubles of scratch).  Needs blockDim.x >= max(32, nA).  Returns (in every thread) whether A was positive definite.
+__device__ inline bool wls_factor_invert(double* A, int nA, double* __restrict__ chol, double* __restrict__ ainv) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
     __syncthreads();
     if (threadIdx.x < 32) {
         bool ok = wls_cholesky_warp(A, nA);
-        if (!ok && threadIdx.x == 0) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
+        if (!ok) s_ok = 0;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) chol[idx] = A[idx];
+    if (chol != nullptr)
+        for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) chol[idx] = A[idx];
     // inverse of E^T W E (what upstream's np.linalg.inv computes): column c of the inverse solves L L^T x = e_c
     if ((int)threadIdx.x < nA) {
         const int c = threadIdx.x;
@@ -392,8 +391,34 @@ __global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double*
             for (int k = r + 1; k < nA; ++k) v -= A[k * nA + r] * x[k];
             x[r] = v / A[r * nA + r];
         }
-        for (int r = 0; r < nA; ++r) ainv[r * nA + c] = x[r];
+        if (ainv != nullptr)
+            for (int r = 0; r < nA; ++r) ainv[r * nA + c] = x[r];
     }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// factor the normal matrix of a shared plan once (dks_set_shared_plan): one CTA
+__global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int S, int M,
+                                   double* __restrict__ chol, double* __restrict__ ainv, int* __restrict__ status) {
+    extern __shared__ double sm_d[];
+    double* A = sm_d;
+    const int nA = M - 1;
+    wls_build_normal(z, w, S, M, A, threadIdx.x >> 5, blockDim.x >> 5);
+    __syncthreads();
+    const bool ok = wls_factor_invert(A, nA, chol, ainv);
+    if (!ok && threadIdx.x == 0) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
+}
+
+// normal matrix of the first `rows` rows of a plan (its enumerated prefix), unfactored: the per-instance sampler adds
+// the sampled rows' part to it
+__global__ void plan_prefix_normal_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int rows, int M,
+                                          double* __restrict__ afix) {
+    extern __shared__ double sm_d[];
+    const int nA = M - 1;
+    wls_build_normal(z, w, rows, M, sm_d, threadIdx.x >> 5, blockDim.x >> 5);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) afix[idx] = sm_d[idx];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -456,6 +481,7 @@ __global__ void __launch_bounds__(256) explain_simt_kernel(ExplainParams p) {
         if (p.ext_z != nullptr) {
             zp = p.ext_z + (size_t)i * p.ext_stride;
             wp = p.ext_w + (size_t)i * p.ext_stride;
+            if (p.ext_chol != nullptr) chol = p.ext_chol + (size_t)i * p.ext_fstride;   // factored with the plan
         } else {
             PlanDev pd = p.plans[M];
             if (pd.z == nullptr || pd.S != S) {

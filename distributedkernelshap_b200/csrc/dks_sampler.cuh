@@ -3,26 +3,32 @@
 // Upstream draws a fresh plan for every instance from an advancing MT19937 stream.  Here every instance gets its own
 // plan from a counter-based generator, Philox4x32-10 keyed by the seed with counter (draw t, global row, block), so the
 // plan of a row does not depend on batching, sharding or the number of GPUs.  The sequential semantics are upstream's:
-//   draw t: subset size ~ p (sizes not fully enumerated), then a uniform subset of that size;
+//   draw t: subset size ~ p (sizes not fully enumerated), then a uniform subset of that size (Floyd's algorithm);
 //   a mask seen before adds 1 to the weight of its first occurrence (and of its complement row);
 //   a new mask takes the next row, followed by its complement when the size is "paired" and a row is left;
 //   stop when the budget S is filled; sampled weights are rescaled to the mass the enumerated sizes left over.
 // The enumerated prefix (deterministic per M) is copied from the shared plan of that M.  One CTA per instance: draws are
-// produced in batches of 1024, first occurrences resolved with a shared-memory hash table (atomicMin on the draw index),
-// row positions with a block prefix sum -- the result is independent of thread scheduling.
-// tests/sampler_twin.py is the NumPy twin; tests compare the plans bit for bit.
+// produced in batches, first occurrences resolved with a shared-memory hash table (atomicMin on the draw index), row
+// positions with a block prefix sum -- the result is independent of thread scheduling and of the batch sizes.
+//
+// The same CTA then prepares the instance's regression: E^T W E = (prefix part, precomputed per M) + scale * (integer
+// co-occurrence counts of the sampled rows).  The counts come from the bit-transposed plan -- ballots turn 32 rows into
+// one word per column, AND + popc count 32 rows per instruction, multiplicities enter through their bit planes -- and
+// the matrix is Cholesky-factored and inverted here, so the explain kernels only do the mat-vec.
+// tests/sampler_twin.py is the NumPy twin of the random stream; tests compare the plans bit for bit.
 #pragma once
 
 #include "dks_common.cuh"
+#include "dks_kernels.cuh"
 
 namespace dks {
 namespace sampler {
 
 constexpr int THREADS = 256;
+constexpr int NWARPS = THREADS / 32;
 constexpr int DRAWS_PER_THREAD = 4;
 constexpr int BATCH = THREADS * DRAWS_PER_THREAD;
-constexpr int MAX_SAMPLED = 4096;          // rows the sampled part of a plan may have
-constexpr int TABLE_CAP = 2 * MAX_SAMPLED; // hash table slots (power of two)
+constexpr int MAX_SAMPLED = 4096;          // rows the sampled part of a plan may have (multiplicities stay < 2^15)
 
 using SamplingInfo = ::DksSamplingInfo;
 
@@ -38,14 +44,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// position (from the LSB) of the r-th (0-based) set bit of x
-__device__ __forceinline__ int nth_set_bit(uint64_t x, int r) {
-    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-    const int clo = __popc(lo);
-    if (r < clo) return (int)__fns(lo, 0, r + 1);
-    return 32 + (int)__fns(hi, 0, r - clo + 1);
-}
-
 __device__ __forceinline__ uint32_t hash_mask(uint64_t m) {
     m ^= m >> 33; m *= 0xff51afd7ed558ccdull; m ^= m >> 33; m *= 0xc4ceb9fe1a85ec53ull; m ^= m >> 33;
     return (uint32_t)m;
@@ -53,25 +51,39 @@ __device__ __forceinline__ uint32_t hash_mask(uint64_t m) {
 
 struct SamplerParams {
     int n, G, S_req, stride;
+    int table_cap;                  // hash table slots (power of two >= 2 * max_left, >= 256)
+    int max_left;                   // most sampled rows any plan of this launch can have (multiple of 32)
+    int fstride;                    // doubles per instance in out_chol / out_ainv
     uint64_t seed;
     long long row_offset;           // global index of row 0 of this call
     const int* Mcnt;
     const PlanDev* plans;           // shared plans: source of the enumerated prefix
     const SamplingInfo* info;       // [DKS_MAX_GROUPS + 1]
+    const double* const* afix;      // [DKS_MAX_GROUPS + 1] normal matrix of the enumerated prefix
     uint64_t* out_z;                // [n][stride]
     double* out_w;                  // [n][stride]
+    double* out_chol;               // [n][fstride] Cholesky factor of E^T W E
+    double* out_ainv;               // [n][fstride] its inverse
     int* status;
 };
 
+inline size_t smem_bytes(int table_cap, int max_left, int G) {
+    const size_t nA = G > 1 ? G - 1 : 1;
+    return (size_t)table_cap * (8 + 4 + 4) + (size_t)max_left * 4 + 2 * nA * nA * sizeof(double);
+}
+
 __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    uint64_t* tkey = reinterpret_cast<uint64_t*>(smraw);                 // [TABLE_CAP]
-    uint32_t* tfirst = reinterpret_cast<uint32_t*>(tkey + TABLE_CAP);     // [TABLE_CAP] first draw index
-    uint32_t* tcount = tfirst + TABLE_CAP;                                // [TABLE_CAP] multiplicity among counted draws
-    uint32_t* rowslot = tcount + TABLE_CAP;                               // [MAX_SAMPLED] table slot of each sampled row
-    __shared__ uint32_t s_warp[THREADS / 32];
-    __shared__ uint32_t s_carry;
-    __shared__ double s_red[THREADS / 32];
+    const int cap = p.table_cap;
+    uint64_t* tkey = reinterpret_cast<uint64_t*>(smraw);                 // [cap]
+    uint32_t* tfirst = reinterpret_cast<uint32_t*>(tkey + cap);           // [cap] first draw index
+    uint32_t* tcount = tfirst + cap;                                      // [cap] multiplicity among counted draws
+    uint32_t* rowslot = tcount + cap;                                     // [max_left] table slot of each sampled row
+    double* Abuf = reinterpret_cast<double*>(rowslot + p.max_left);       // [2][nA*nA] normal matrix + scratch
+    uint32_t* colbits = reinterpret_cast<uint32_t*>(tkey);                // aliases tkey once the draws are done
+    __shared__ uint32_t s_warp[NWARPS];
+    __shared__ uint32_t s_carry, s_maxcnt;
+    __shared__ double s_red[NWARPS];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 
     for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
@@ -81,134 +93,209 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
         if (M < 2) continue;
         const int S = dks_effective_S(M, p.S_req);
         const PlanDev pd = p.plans[M];
-        if (pd.z == nullptr || pd.S != S || S > p.stride) {
+        if (pd.z == nullptr || pd.S != S || S > p.stride || p.afix[M] == nullptr) {
             if (tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_PLAN_MISSING) == 0) p.status[1] = M; }
             for (int s = tid; s < p.stride; s += THREADS) { oz[s] = 0ull; ow[s] = 0.0; }
             continue;
         }
         const SamplingInfo& inf = p.info[M];
-        const int nfixed = inf.nfixed, left0 = S - nfixed;
+        const int nfixed = inf.nfixed;
+        const int left0 = inf.ncdf > 0 ? S - nfixed : 0;
+        if (left0 > p.max_left) {
+            if (tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_UNSUPPORTED) == 0) p.status[1] = M; }
+            for (int s = tid; s < p.stride; s += THREADS) { oz[s] = 0ull; ow[s] = 0.0; }
+            continue;
+        }
         // enumerated prefix (deterministic per M); the rest starts empty
         for (int s = tid; s < S; s += THREADS) {
             oz[s] = s < nfixed ? pd.z[s] : 0ull;
             ow[s] = s < nfixed ? pd.w[s] : 0.0;
         }
-        if (left0 <= 0 || inf.ncdf <= 0) continue;
-        if (left0 > MAX_SAMPLED) {
-            if (tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_UNSUPPORTED) == 0) p.status[1] = M; }
-            continue;
-        }
-        __syncthreads();
-        for (int h = tid; h < TABLE_CAP; h += THREADS) { tkey[h] = 0ull; tfirst[h] = 0xFFFFFFFFu; tcount[h] = 0u; }
-        if (tid == 0) s_carry = 0u;
-        __syncthreads();
-
         const uint64_t fullmask = M >= 64 ? ~0ull : ((1ull << M) - 1ull);
-        const uint64_t grow = (uint64_t)(p.row_offset + i);
-        const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-        const uint32_t ndraws = 4u * (uint32_t)left0;            // upstream draws 4 * samples_left size picks at most
+        uint32_t filled = 0u;
+        double scale = 0.0;
+        __syncthreads();
+        if (left0 > 0) {
+            for (int h = tid; h < cap; h += THREADS) { tkey[h] = 0ull; tfirst[h] = 0xFFFFFFFFu; tcount[h] = 0u; }
+            if (tid == 0) s_carry = 0u;
+            __syncthreads();
 
-        for (uint32_t t0 = 0; t0 < ndraws; t0 += BATCH) {
-            uint64_t mask[DRAWS_PER_THREAD];
-            uint32_t slot[DRAWS_PER_THREAD];
-            bool paired[DRAWS_PER_THREAD], valid[DRAWS_PER_THREAD];
-            // ---- 1. generate this thread's draws (consecutive t) and register first occurrences
+            const uint64_t grow = (uint64_t)(p.row_offset + i);
+            const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+            const uint32_t ndraws = 4u * (uint32_t)left0;        // upstream draws 4 * samples_left size picks at most
+            uint32_t t0 = 0u;
+            while (t0 < ndraws) {
+                // draws of this batch: about what the rows still missing need (a draw yields up to two rows)
+                const uint32_t missing = (uint32_t)left0 - s_carry;
+                uint32_t bsz = missing - missing / 3u + 32u;
+                bsz = (bsz + DRAWS_PER_THREAD * 32u - 1u) / (DRAWS_PER_THREAD * 32u) * (DRAWS_PER_THREAD * 32u);
+                if (bsz > (uint32_t)BATCH) bsz = BATCH;
+                const uint32_t tend = min(ndraws, t0 + bsz);
+                uint64_t mask[DRAWS_PER_THREAD];
+                uint32_t slot[DRAWS_PER_THREAD];
+                bool paired[DRAWS_PER_THREAD], valid[DRAWS_PER_THREAD];
+                // ---- 1. generate this thread's draws (consecutive t) and register first occurrences
 #pragma unroll
-            for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
-                const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
-                valid[j] = t < ndraws;
-                mask[j] = 0ull; slot[j] = 0u; paired[j] = false;
-                if (!valid[j]) continue;
-                uint32_t rnd[4];
-                philox4x32_10(k0, k1, t, (uint32_t)grow, (uint32_t)(grow >> 32), 0u, rnd);
-                const double u = ((double)rnd[0] + 0.5) * 2.3283064365386963e-10;     // (r + 1/2) / 2^32
-                int idx = 0;
-                while (idx < inf.ncdf - 1 && u >= inf.cdf[idx]) ++idx;
-                const int size = idx + inf.n_full + 1;
-                paired[j] = size <= inf.n_paired;
-                uint64_t avail = fullmask, mk = 0ull;
-                int have = 1;                                     // rnd[1..3] are still unused
-                uint32_t blockno = 0u;
-                for (int c = 0; c < size; ++c) {
-                    if (have == 4) { ++blockno; philox4x32_10(k0, k1, t, (uint32_t)grow, (uint32_t)(grow >> 32), blockno, rnd); have = 0; }
-                    const uint32_t r32 = rnd[have++];
-                    const int pick = (int)(((uint64_t)r32 * (uint64_t)(M - c)) >> 32);
-                    const int bit = nth_set_bit(avail, pick);
-                    mk |= 1ull << bit;
-                    avail &= ~(1ull << bit);
+                for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
+                    const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
+                    valid[j] = t < tend;
+                    mask[j] = 0ull; slot[j] = 0u; paired[j] = false;
+                    if (!valid[j]) continue;
+                    uint32_t rnd[4];
+                    philox4x32_10(k0, k1, t, (uint32_t)grow, (uint32_t)(grow >> 32), 0u, rnd);
+                    const double u = ((double)rnd[0] + 0.5) * 2.3283064365386963e-10;     // (r + 1/2) / 2^32
+                    int idx = 0;
+                    while (idx < inf.ncdf - 1 && u >= inf.cdf[idx]) ++idx;
+                    const int size = idx + inf.n_full + 1;
+                    paired[j] = size <= inf.n_paired;
+                    // uniform subset of `size` of the M positions (Floyd): for j2 = M-size .. M-1 pick in [0, j2]
+                    uint64_t mk = 0ull;
+                    int have = 1;                                     // rnd[1..3] are still unused
+                    uint32_t blockno = 0u;
+                    for (int j2 = M - size; j2 < M; ++j2) {
+                        if (have == 4) {
+                            ++blockno;
+                            philox4x32_10(k0, k1, t, (uint32_t)grow, (uint32_t)(grow >> 32), blockno, rnd);
+                            have = 0;
+                        }
+                        const uint32_t r32 = have == 0 ? rnd[0] : have == 1 ? rnd[1] : have == 2 ? rnd[2] : rnd[3];
+                        ++have;
+                        const int pick = (int)(((uint64_t)r32 * (uint64_t)(j2 + 1)) >> 32);
+                        const int bit = ((mk >> pick) & 1ull) ? j2 : pick;
+                        mk |= 1ull << bit;
+                    }
+                    mask[j] = mk;
+                    uint32_t h = hash_mask(mk) & (uint32_t)(cap - 1);
+                    while (true) {
+                        const unsigned long long old =
+                            atomicCAS(reinterpret_cast<unsigned long long*>(&tkey[h]), 0ull, (unsigned long long)mk);
+                        if (old == 0ull || old == (unsigned long long)mk) break;
+                        h = (h + 1) & (uint32_t)(cap - 1);
+                    }
+                    slot[j] = h;
+                    atomicMin(&tfirst[h], t);
                 }
-                mask[j] = mk;
-                uint32_t h = hash_mask(mk) & (TABLE_CAP - 1);
-                while (true) {
-                    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&tkey[h]), 0ull, (unsigned long long)mk);
-                    if (old == 0ull || old == (unsigned long long)mk) break;
-                    h = (h + 1) & (TABLE_CAP - 1);
+                __syncthreads();
+                // ---- 2. rows each draw would create, exclusive prefix over the batch in draw order
+                uint32_t rows[DRAWS_PER_THREAD], local = 0u;
+#pragma unroll
+                for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
+                    const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
+                    const bool fresh = valid[j] && tfirst[slot[j]] == t;
+                    rows[j] = fresh ? (paired[j] ? 2u : 1u) : 0u;
+                    local += rows[j];
                 }
-                slot[j] = h;
-                atomicMin(&tfirst[h], t);
-            }
-            __syncthreads();
-            // ---- 2. rows each draw would create, exclusive prefix over the batch in draw order
-            uint32_t rows[DRAWS_PER_THREAD], local = 0u;
+                uint32_t incl = local;
 #pragma unroll
-            for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
-                const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
-                const bool fresh = valid[j] && tfirst[slot[j]] == t;
-                rows[j] = fresh ? (paired[j] ? 2u : 1u) : 0u;
-                local += rows[j];
-            }
-            uint32_t incl = local;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_warp[wib] = incl;
+                __syncthreads();
+                uint32_t warp_off = 0u, total = 0u;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) s_warp[wib] = incl;
-            __syncthreads();
-            uint32_t warp_off = 0u, total = 0u;
+                for (int wq = 0; wq < NWARPS; ++wq) { if (wq < wib) warp_off += s_warp[wq]; total += s_warp[wq]; }
+                const uint32_t carry = s_carry;
+                uint32_t before = carry + warp_off + incl - local;    // rows created by earlier draws
+                // ---- 3. draws made while the budget was not yet full count; new masks among them take rows
 #pragma unroll
-            for (int wq = 0; wq < THREADS / 32; ++wq) { if (wq < wib) warp_off += s_warp[wq]; total += s_warp[wq]; }
-            const uint32_t carry = s_carry;
-            uint32_t before = carry + warp_off + incl - local;    // rows created by earlier draws
-            // ---- 3. draws made while the budget was not yet full count; new masks among them take rows
-#pragma unroll
-            for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
-                if (valid[j] && before < (uint32_t)left0) {
-                    atomicAdd(&tcount[slot[j]], 1u);
-                    if (rows[j] > 0u) {
-                        oz[nfixed + before] = mask[j];
-                        rowslot[before] = slot[j];
-                        if (rows[j] == 2u && before + 1u < (uint32_t)left0) {
-                            oz[nfixed + before + 1u] = mask[j] ^ fullmask;
-                            rowslot[before + 1u] = slot[j];
+                for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
+                    if (valid[j] && before < (uint32_t)left0) {
+                        atomicAdd(&tcount[slot[j]], 1u);
+                        if (rows[j] > 0u) {
+                            oz[nfixed + before] = mask[j];
+                            rowslot[before] = slot[j];
+                            if (rows[j] == 2u && before + 1u < (uint32_t)left0) {
+                                oz[nfixed + before + 1u] = mask[j] ^ fullmask;
+                                rowslot[before + 1u] = slot[j];
+                            }
                         }
                     }
+                    before += rows[j];
                 }
-                before += rows[j];
+                __syncthreads();
+                if (tid == 0) s_carry = carry + total;
+                __syncthreads();
+                t0 = tend;
+                if (carry + total >= (uint32_t)left0) break;
             }
+            // ---- 4. weights: multiplicity of the row's mask, rescaled to the mass left for the sampled sizes
+            filled = min(s_carry, (uint32_t)left0);
+            double part = 0.0;
+            uint32_t mx = 0u;
+            for (uint32_t r = tid; r < filled; r += THREADS) {
+                const uint32_t c = tcount[rowslot[r]];
+                part += (double)c;
+                mx = max(mx, c);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                part += __shfl_xor_sync(0xffffffffu, part, o);
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (lane == 0) { s_red[wib] = part; s_warp[wib] = mx; }
             __syncthreads();
-            if (tid == 0) s_carry = carry + total;
+            double totalw = 0.0;
+            uint32_t maxcnt = 0u;
+#pragma unroll
+            for (int wq = 0; wq < NWARPS; ++wq) { totalw += s_red[wq]; maxcnt = max(maxcnt, s_warp[wq]); }
+            scale = totalw > 0.0 ? inf.weight_left / totalw : 0.0;
+            for (uint32_t r = tid; r < filled; r += THREADS) ow[nfixed + r] = (double)tcount[rowslot[r]] * scale;
+            if (tid == 0) s_maxcnt = maxcnt;
             __syncthreads();
-            if (carry + total >= (uint32_t)left0) break;
         }
-        // ---- 4. weights: multiplicity of the row's mask, rescaled to the mass left for the sampled sizes
-        const uint32_t filled = min(s_carry, (uint32_t)left0);
-        double part = 0.0;
-        for (uint32_t r = tid; r < filled; r += THREADS) part += (double)tcount[rowslot[r]];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) s_red[wib] = part;
+
+        // ---- 5. E^T W E of the instance: prefix part + scale * integer co-occurrence counts of the sampled rows.
+        // e_k = z_k - z_L, and e_k e_l = [bits k and l set in z'] with z' = z_L ? ~z : z
+        const int nA = M - 1, L = M - 1;
+        const int ngroups = ((int)filled + 31) / 32;
+        const int nplanes = filled ? 32 - __clz(s_maxcnt) : 0;
+        uint32_t* planes = colbits + (size_t)nA * ngroups;           // [nplanes][ngroups] bit planes of the multiplicity
+        for (int g = wib; g < ngroups; g += NWARPS) {                // the hash keys are dead: colbits may overwrite them
+            const uint32_t r = (uint32_t)g * 32u + lane;
+            uint64_t zr = 0ull;
+            uint32_t cnt = 0u;
+            if (r < filled) {
+                zr = oz[nfixed + r];
+                if ((zr >> L) & 1ull) zr = ~zr;
+                cnt = tcount[rowslot[r]];
+            }
+            for (int k = 0; k < nA; ++k) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (zr >> k) & 1ull);
+                if (lane == 0) colbits[(size_t)k * ngroups + g] = b;
+            }
+            for (int b2 = 0; b2 < nplanes; ++b2) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (cnt >> b2) & 1u);
+                if (lane == 0) planes[(size_t)b2 * ngroups + g] = b;
+            }
+        }
         __syncthreads();
-        double totalw = 0.0;
+        const double* afix = p.afix[M];
+        const int npairs = nA * (nA + 1) / 2;
+        for (int pr = wib; pr < npairs; pr += NWARPS) {
+            int k = 0, rem = pr;
+            while (rem > k) { rem -= (k + 1); ++k; }              // pr = k(k+1)/2 + l, l <= k
+            const int l = rem;
+            uint32_t acc = 0u;
+            for (int g = lane; g < ngroups; g += 32) {
+                const uint32_t both = colbits[(size_t)k * ngroups + g] & colbits[(size_t)l * ngroups + g];
+                for (int b2 = 0; b2 < nplanes; ++b2) acc += (uint32_t)__popc(both & planes[(size_t)b2 * ngroups + g]) << b2;
+            }
 #pragma unroll
-        for (int wq = 0; wq < THREADS / 32; ++wq) totalw += s_red[wq];
-        const double scale = totalw > 0.0 ? inf.weight_left / totalw : 0.0;
-        for (uint32_t r = tid; r < filled; r += THREADS) ow[nfixed + r] = (double)tcount[rowslot[r]] * scale;
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const double v = afix[k * nA + l] + scale * (double)acc;
+                Abuf[k * nA + l] = v;
+                Abuf[l * nA + k] = v;
+            }
+        }
+        __syncthreads();
+        const bool ok = wls_factor_invert(Abuf, nA, p.out_chol + (size_t)i * p.fstride, p.out_ainv + (size_t)i * p.fstride);
+        if (!ok && tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
         __syncthreads();
     }
 }
-
-inline size_t smem_bytes() { return (size_t)TABLE_CAP * (8 + 4 + 4) + (size_t)MAX_SAMPLED * 4; }
 
 }  // namespace sampler
 }  // namespace dks

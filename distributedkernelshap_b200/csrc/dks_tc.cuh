@@ -741,11 +741,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) explain_tcgen05_kernel(TcParams t
                 zp = p.ext_z + (size_t)i * p.ext_stride;
                 wp = p.ext_w + (size_t)i * p.ext_stride;
                 named_bar_sync(1, WLS_THREADS);
-                wls_build_normal(zp, wp, S, M, sm.chol, ww, N_WLS_WARPS);
-                named_bar_sync(1, WLS_THREADS);
-                if (ww == 0) {
-                    bool ok = wls_cholesky_warp(sm.chol, nA);
-                    if (!ok && lane == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
+                if (p.ext_ainv != nullptr) {             // the plan came with the inverse of its normal matrix
+                    const double* ainv = p.ext_ainv + (size_t)i * p.ext_fstride;
+                    for (int idx = wtid; idx < nA * nA; idx += WLS_THREADS) sm.chol[idx] = ainv[idx];
+                    have_inverse = true;
+                } else {
+                    wls_build_normal(zp, wp, S, M, sm.chol, ww, N_WLS_WARPS);
+                    named_bar_sync(1, WLS_THREADS);
+                    if (ww == 0) {
+                        bool ok = wls_cholesky_warp(sm.chol, nA);
+                        if (!ok && lane == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
+                    }
                 }
             }
             const double delta = p.dlink[(size_t)i * C + 1];

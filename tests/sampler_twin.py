@@ -24,14 +24,32 @@ def philox4x32_10(key, ctr):
     return c0, c1, c2, c3
 
 
-def nth_set_bit(x, r):
-    pos = 0
-    while True:
-        if (x >> pos) & 1:
-            if r == 0:
-                return pos
-            r -= 1
-        pos += 1
+class _LazySubset:
+    """What ``permutation(M)`` returns: only ``[:size]`` is ever taken from it, and the size-``size`` subset is drawn
+    the way the device draws it (Floyd's algorithm: for j = M-size .. M-1 pick t uniform in [0, j]; take j if t is
+    already in the set, else t)."""
+
+    def __init__(self, stream, t, M):
+        self.stream, self.t, self.M = stream, t, M
+
+    def __getitem__(self, sl):
+        assert isinstance(sl, slice) and sl.start is None and sl.step is None
+        size, M, t = sl.stop, self.M, self.t
+        rnd = list(self.stream._block(t, 0))
+        have, block = 1, 0
+        chosen, members = 0, []
+        for j in range(M - size, M):
+            if have == 4:
+                block += 1
+                rnd = list(self.stream._block(t, block))
+                have = 0
+            r32 = rnd[have]
+            have += 1
+            pick = (r32 * (j + 1)) >> 32
+            bit = j if (chosen >> pick) & 1 else pick
+            chosen |= 1 << bit
+            members.append(bit)
+        return np.array(members, dtype=np.int64)
 
 
 class PhiloxPlanStream:
@@ -52,19 +70,4 @@ class PhiloxPlanStream:
     def permutation(self, M):
         t = self.t
         self.t += 1
-        rnd = list(self._block(t, 0))
-        have, block = 1, 0
-        avail = (1 << M) - 1
-        out = []
-        for c in range(M):
-            if have == 4:
-                block += 1
-                rnd = list(self._block(t, block))
-                have = 0
-            r32 = rnd[have]
-            have += 1
-            pick = (r32 * (M - c)) >> 32
-            bit = nth_set_bit(avail, pick)
-            out.append(bit)
-            avail &= ~(1 << bit)
-        return np.array(out)
+        return _LazySubset(self, t, M)

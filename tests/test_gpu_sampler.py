@@ -33,7 +33,8 @@ def _expected_plan(M, nsamples, seed, row):
 def test_device_plans_equal_the_sequential_loop_on_the_same_stream(widths, nsamples):
     prob = make_problem(seed=21, n=12, N=10, widths=widths)
     eng = _engine(prob, kernel="simt", seed=77, plan_mode="per_instance")
-    eng.shap_values(prob["X"], nsamples=nsamples, l1_reg=False)
+    orc = _oracle(prob)
+    got = eng.shap_values(prob["X"], nsamples=nsamples, l1_reg=False)
     zb, w = eng.instance_plans()
     Ms, _ = eng.varying(prob["X"])
     assert zb.shape[0] == prob["X"].shape[0]
@@ -43,6 +44,13 @@ def test_device_plans_equal_the_sequential_loop_on_the_same_stream(widths, nsamp
         np.testing.assert_array_equal(zb[i, :S], want_z, err_msg=f"instance {i}")
         np.testing.assert_allclose(w[i, :S], want_w, rtol=1e-13, atol=0)
         assert np.all(w[i, S:] == 0)
+        # the regression prepared with the plan (normal matrix from popcounts of the bit-transposed rows, factored in
+        # the sampler kernel) must give the oracle's phi for that plan
+        k = np.arange(int(M), dtype=np.uint64)
+        Z = ((want_z[:, None] >> k[None, :]) & np.uint64(1)).astype(np.uint8)
+        phi = orc.explain(prob["X"][i:i + 1], plan=(Z, want_w), nsamples=nsamples, l1_reg=False)
+        for c in range(2):
+            assert rel_err(got[c][i], phi[:, c]) < TOL
 
 
 @pytest.mark.parametrize("kernel", ["simt", "tcgen05", "auto"])
