@@ -144,8 +144,8 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (max_left > dks::sampler::MAX_SAMPLED)
             return fail(DKS_ERR_UNSUPPORTED, "per-instance plans: %d sampled rows per plan exceed the sampler's limit of %d",
                         max_left, dks::sampler::MAX_SAMPLED);
-        int cap = 256;
-        while (cap < 2 * max_left) cap <<= 1;
+        int cap = 256;                       // hash slots; its arrays are reused for the bit-transposed plan and pair counts
+        while (cap < 2 * max_left || cap < nAmax * (nAmax + 1) / 2) cap <<= 1;
         dks::sampler::SamplerParams sp;
         sp.n = n; sp.G = ctx->G; sp.S_req = ctx->nsamples_req; sp.stride = stride; sp.seed = ctx->sampler_seed;
         sp.table_cap = cap; sp.max_left = max_left; sp.fstride = fstride;
@@ -162,7 +162,19 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (per_sm < 1) per_sm = 1;
         const int sgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;
         dks::sampler::sample_plans_kernel<<<sgrid, dks::sampler::THREADS, ssm, ctx->stream>>>(sp);
-        ctx->launches += 1;
+        {
+            const size_t per_warp = (size_t)2 * nAmax * nAmax * sizeof(double);
+            int fw = (int)((size_t)ctx->max_smem_optin / per_warp);
+            if (fw > dks::sampler::FACTOR_WARPS) fw = dks::sampler::FACTOR_WARPS;
+            if (fw < 1)
+                return fail(DKS_ERR_UNSUPPORTED, "per-instance plans: normal-matrix workspace does not fit shared memory");
+            const size_t fsm = (size_t)fw * per_warp;
+            CUDA_TRY(cudaFuncSetAttribute(dks::sampler::factor_plans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            int fgrid = (n + fw - 1) / fw;
+            dks::sampler::factor_plans_kernel<<<fgrid, fw * 32, fsm, ctx->stream>>>(n, ctx->d_M, fstride, ctx->d_genchol,
+                                                                                    ctx->d_genainv, nAmax, ctx->d_status);
+        }
+        ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
         ctx->gen_stride = stride; ctx->gen_n = n;
         ext_z = ctx->d_genz; ext_w = ctx->d_genw; ext_stride = stride;

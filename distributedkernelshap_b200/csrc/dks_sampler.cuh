@@ -49,6 +49,20 @@ __device__ __forceinline__ uint32_t hash_mask(uint64_t m) {
     return (uint32_t)m;
 }
 
+// 32 x 32 bit-matrix transpose across the lanes of a warp (5 butterfly stages).  With x_r the word of lane r, lane i ends
+// up with bit p = bit (31 - i) of x_(31-p): column c of the block sits in lane 31 - c, row r at bit 31 - r.
+__device__ __forceinline__ uint32_t bit_transpose32(uint32_t x, int lane) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, x, j);
+        if (lane & j) x ^= ((other ^ (x >> j)) & m) << j;       // upper lane of the pair: takes the partner's low block
+        else x ^= (x ^ (other >> j)) & m;                         // lower lane: takes the partner's high block
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
 struct SamplerParams {
     int n, G, S_req, stride;
     int table_cap;                  // hash table slots (power of two >= 2 * max_left, >= 256)
@@ -84,6 +98,7 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
     __shared__ uint32_t s_warp[NWARPS];
     __shared__ uint32_t s_carry, s_maxcnt;
     __shared__ double s_red[NWARPS];
+    __shared__ double s_cdf[32];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 
     for (int i = blockIdx.x; i < p.n; i += gridDim.x) {
@@ -112,6 +127,8 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
             ow[s] = s < nfixed ? pd.w[s] : 0.0;
         }
         const uint64_t fullmask = M >= 64 ? ~0ull : ((1ull << M) - 1ull);
+        if (tid < 32) s_cdf[tid] = tid < inf.ncdf ? inf.cdf[tid] : 2.0;
+        const int ncdf = inf.ncdf, n_full = inf.n_full, n_paired = inf.n_paired;
         uint32_t filled = 0u;
         double scale = 0.0;
         __syncthreads();
@@ -128,26 +145,26 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
                 // draws of this batch: about what the rows still missing need (a draw yields up to two rows)
                 const uint32_t missing = (uint32_t)left0 - s_carry;
                 uint32_t bsz = missing - missing / 3u + 32u;
-                bsz = (bsz + DRAWS_PER_THREAD * 32u - 1u) / (DRAWS_PER_THREAD * 32u) * (DRAWS_PER_THREAD * 32u);
                 if (bsz > (uint32_t)BATCH) bsz = BATCH;
                 const uint32_t tend = min(ndraws, t0 + bsz);
+                const uint32_t dpt = (tend - t0 + THREADS - 1u) / THREADS;     // draws per thread in this batch (<= 4)
                 uint64_t mask[DRAWS_PER_THREAD];
                 uint32_t slot[DRAWS_PER_THREAD];
                 bool paired[DRAWS_PER_THREAD], valid[DRAWS_PER_THREAD];
                 // ---- 1. generate this thread's draws (consecutive t) and register first occurrences
 #pragma unroll
                 for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
-                    const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
-                    valid[j] = t < tend;
+                    const uint32_t t = t0 + (uint32_t)tid * dpt + j;
+                    valid[j] = (uint32_t)j < dpt && t < tend;
                     mask[j] = 0ull; slot[j] = 0u; paired[j] = false;
                     if (!valid[j]) continue;
                     uint32_t rnd[4];
                     philox4x32_10(k0, k1, t, (uint32_t)grow, (uint32_t)(grow >> 32), 0u, rnd);
                     const double u = ((double)rnd[0] + 0.5) * 2.3283064365386963e-10;     // (r + 1/2) / 2^32
                     int idx = 0;
-                    while (idx < inf.ncdf - 1 && u >= inf.cdf[idx]) ++idx;
-                    const int size = idx + inf.n_full + 1;
-                    paired[j] = size <= inf.n_paired;
+                    while (idx < ncdf - 1 && u >= s_cdf[idx]) ++idx;
+                    const int size = idx + n_full + 1;
+                    paired[j] = size <= n_paired;
                     // uniform subset of `size` of the M positions (Floyd): for j2 = M-size .. M-1 pick in [0, j2]
                     uint64_t mk = 0ull;
                     int have = 1;                                     // rnd[1..3] are still unused
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
                 uint32_t rows[DRAWS_PER_THREAD], local = 0u;
 #pragma unroll
                 for (int j = 0; j < DRAWS_PER_THREAD; ++j) {
-                    const uint32_t t = t0 + (uint32_t)tid * DRAWS_PER_THREAD + j;
+                    const uint32_t t = t0 + (uint32_t)tid * dpt + j;
                     const bool fresh = valid[j] && tfirst[slot[j]] == t;
                     rows[j] = fresh ? (paired[j] ? 2u : 1u) : 0u;
                     local += rows[j];
@@ -247,11 +264,17 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
         }
 
         // ---- 5. E^T W E of the instance: prefix part + scale * integer co-occurrence counts of the sampled rows.
-        // e_k = z_k - z_L, and e_k e_l = [bits k and l set in z'] with z' = z_L ? ~z : z
+        // e_k = z_k - z_L, and e_k e_l = [bits k and l set in z'] with z' = z_L ? ~z : z.  Each warp transposes 32 rows
+        // at a time (bit_transpose32: afterwards lane 31-c holds column c of the 32 x 32 bit block, rows in a fixed
+        // permuted bit order that is the same for every word transposed), so a column pair is counted 32 rows per popc.
         const int nA = M - 1, L = M - 1;
         const int ngroups = ((int)filled + 31) / 32;
+        const int cstride = ngroups | 1;                                // odd word stride: conflict-free column reads
         const int nplanes = filled ? 32 - __clz(s_maxcnt) : 0;
-        uint32_t* planes = colbits + (size_t)nA * ngroups;           // [nplanes][ngroups] bit planes of the multiplicity
+        uint32_t* planes = colbits + (size_t)nA * cstride;            // [nplanes][cstride] bit planes of the multiplicity
+        int* Aint = reinterpret_cast<int*>(tfirst);                    // [npairs] (first-occurrence indices are dead)
+        const int npairs = nA * (nA + 1) / 2;
+        for (int pr = tid; pr < npairs; pr += THREADS) Aint[pr] = 0;
         for (int g = wib; g < ngroups; g += NWARPS) {                // the hash keys are dead: colbits may overwrite them
             const uint32_t r = (uint32_t)g * 32u + lane;
             uint64_t zr = 0ull;
@@ -261,39 +284,96 @@ __global__ void __launch_bounds__(THREADS) sample_plans_kernel(SamplerParams p) 
                 if ((zr >> L) & 1ull) zr = ~zr;
                 cnt = tcount[rowslot[r]];
             }
-            for (int k = 0; k < nA; ++k) {
-                const uint32_t b = __ballot_sync(0xffffffffu, (zr >> k) & 1ull);
-                if (lane == 0) colbits[(size_t)k * ngroups + g] = b;
+            const int c = 31 - lane;                                  // the column this lane holds after a transpose
+            const uint32_t lo = bit_transpose32((uint32_t)zr, lane);
+            if (c < nA) colbits[(size_t)c * cstride + g] = lo;
+            if (nA > 32) {
+                const uint32_t hi = bit_transpose32((uint32_t)(zr >> 32), lane);
+                if (32 + c < nA) colbits[(size_t)(32 + c) * cstride + g] = hi;
             }
-            for (int b2 = 0; b2 < nplanes; ++b2) {
-                const uint32_t b = __ballot_sync(0xffffffffu, (cnt >> b2) & 1u);
-                if (lane == 0) planes[(size_t)b2 * ngroups + g] = b;
+            const uint32_t pl = bit_transpose32(cnt, lane);
+            if (c < nplanes) planes[(size_t)c * cstride + g] = pl;
+        }
+        __syncthreads();
+        {
+            // work item = (column pair, slice of the row groups); slices keep all threads busy when pairs are few
+            int nsl = THREADS / npairs;
+            if (nsl < 1) nsl = 1;
+            if (nsl > ngroups) nsl = ngroups > 0 ? ngroups : 1;
+            const int per = (ngroups + nsl - 1) / nsl;
+            for (int item = tid; item < npairs * nsl; item += THREADS) {
+                const int pr = item / nsl, sl = item - pr * nsl;
+                int k = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+                while (k * (k + 1) / 2 > pr) --k;
+                while ((k + 1) * (k + 2) / 2 <= pr) ++k;
+                const int l = pr - k * (k + 1) / 2;                  // pr = k(k+1)/2 + l, l <= k
+                const uint32_t* ck = colbits + (size_t)k * cstride;
+                const uint32_t* cl = colbits + (size_t)l * cstride;
+                const int g1 = min(ngroups, (sl + 1) * per);
+                uint32_t acc = 0u;
+                for (int g = sl * per; g < g1; ++g) {
+                    const uint32_t both = ck[g] & cl[g];
+                    for (int b2 = 0; b2 < nplanes; ++b2) acc += (uint32_t)__popc(both & planes[(size_t)b2 * cstride + g]) << b2;
+                }
+                if (acc) atomicAdd(&Aint[pr], (int)acc);
             }
         }
         __syncthreads();
         const double* afix = p.afix[M];
-        const int npairs = nA * (nA + 1) / 2;
-        for (int pr = wib; pr < npairs; pr += NWARPS) {
-            int k = 0, rem = pr;
-            while (rem > k) { rem -= (k + 1); ++k; }              // pr = k(k+1)/2 + l, l <= k
-            const int l = rem;
-            uint32_t acc = 0u;
-            for (int g = lane; g < ngroups; g += 32) {
-                const uint32_t both = colbits[(size_t)k * ngroups + g] & colbits[(size_t)l * ngroups + g];
-                for (int b2 = 0; b2 < nplanes; ++b2) acc += (uint32_t)__popc(both & planes[(size_t)b2 * ngroups + g]) << b2;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                const double v = afix[k * nA + l] + scale * (double)acc;
-                Abuf[k * nA + l] = v;
-                Abuf[l * nA + k] = v;
-            }
+        for (int pr = tid; pr < npairs; pr += THREADS) {
+            int k = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+            while (k * (k + 1) / 2 > pr) --k;
+            while ((k + 1) * (k + 2) / 2 <= pr) ++k;
+            const int l = pr - k * (k + 1) / 2;
+            const double v = afix[k * nA + l] + scale * (double)Aint[pr];
+            Abuf[k * nA + l] = v;
+            Abuf[l * nA + k] = v;
         }
         __syncthreads();
-        const bool ok = wls_factor_invert(Abuf, nA, p.out_chol + (size_t)i * p.fstride, p.out_ainv + (size_t)i * p.fstride);
-        if (!ok && tid == 0) { if (atomicCAS(&p.status[0], 0, DKS_ERR_NUMERIC) == 0) p.status[1] = i; }
+        // the matrix goes out unfactored: factor_plans_kernel (one warp per instance) does the serial part
+        double* Aout = p.out_chol + (size_t)i * p.fstride;
+        for (int idx = tid; idx < nA * nA; idx += THREADS) Aout[idx] = Abuf[idx];
         __syncthreads();
+    }
+}
+
+// Cholesky factor and inverse of every instance's normal matrix, one warp per instance (the chains of square roots and
+// divisions are serial: many instances side by side hide their latency).  chol holds the matrix on entry.
+constexpr int FACTOR_WARPS = 8;
+__global__ void __launch_bounds__(FACTOR_WARPS * 32) factor_plans_kernel(int n, const int* __restrict__ Mcnt, int fstride,
+                                                                         double* __restrict__ chol, double* __restrict__ ainv,
+                                                                         int nAmax, int* __restrict__ status) {
+    extern __shared__ double fsm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* A = fsm + (size_t)wib * 2 * nAmax * nAmax;       // [nA*nA] matrix, then nA*nA of scratch
+    const int nw = blockDim.x >> 5;
+    for (int i = blockIdx.x * nw + wib; i < n; i += gridDim.x * nw) {
+        const int M = Mcnt[i];
+        if (M < 2) continue;
+        const int nA = M - 1;
+        double* ci = chol + (size_t)i * fstride;
+        double* ai = ainv + (size_t)i * fstride;
+        for (int idx = lane; idx < nA * nA; idx += 32) A[idx] = ci[idx];
+        __syncwarp();
+        const bool ok = wls_cholesky_warp(A, nA);
+        if (!ok && lane == 0) { if (atomicCAS(&status[0], 0, DKS_ERR_NUMERIC) == 0) status[1] = i; }
+        __syncwarp();
+        for (int idx = lane; idx < nA * nA; idx += 32) ci[idx] = A[idx];
+        for (int c = lane; c < nA; c += 32) {               // column c of the inverse solves L L^T x = e_c
+            double* x = A + nA * nA + c * nA;
+            for (int r = 0; r < nA; ++r) {
+                double v = (r == c) ? 1.0 : 0.0;
+                for (int k = 0; k < r; ++k) v -= A[r * nA + k] * x[k];
+                x[r] = v / A[r * nA + r];
+            }
+            for (int r = nA - 1; r >= 0; --r) {
+                double v = x[r];
+                for (int k = r + 1; k < nA; ++k) v -= A[k * nA + r] * x[k];
+                x[r] = v / A[r * nA + r];
+            }
+            for (int r = 0; r < nA; ++r) ai[r * nA + c] = x[r];
+        }
+        __syncwarp();
     }
 }
 
