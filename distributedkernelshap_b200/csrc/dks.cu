@@ -219,16 +219,15 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
                       ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->uniform_w && G >= 2 && pg.dmT != nullptr &&
                       pg.S == dks_effective_S(G, ctx->nsamples_req);
     if (kernel == DKS_KERNEL_SHARED && !fast && ext_z == nullptr && pg.z != nullptr)
-        return fail(DKS_ERR_UNSUPPORTED, "shared-plan fast path needs the binary-logistic head, uniform background weights "
-                    "and at most %d background rows", dks::shared_path::MAXN);
+        return fail(DKS_ERR_UNSUPPORTED, "shared-plan fast path needs the binary-logistic head and uniform background weights");
     if (fast) {
         const int S = pg.S, S_pad = pg.S_pad;
         size_t need = (size_t)n * S_pad;
         if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; }
         dks::shared_path::SharedParams sp;
         sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
-        sp.DmT = pg.dmT; sp.z = pg.z; sp.XW = ctx->d_XW; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums;
-        dks::shared_path::launch_explain_shared(sp, ctx->sm_count, ctx->stream);
+        sp.DmT = pg.dmT; sp.z = pg.z; sp.XW = ctx->d_XW; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
+        ctx->launches += dks::shared_path::launch_explain_shared(sp, ctx->sm_count, ctx->stream) - 1;
         dks::shared_path::WlsSharedParams wp;
         wp.n = n; wp.N = ctx->N; wp.G = G; wp.C = ctx->C; wp.S = S; wp.S_pad = S_pad; wp.link = ctx->link;
         wp.uniform_w = 1; wp.sums = ctx->d_sums; wp.z = pg.z; wp.w = pg.w; wp.ainv = pg.ainv; wp.dlink = ctx->d_dlink;
@@ -589,6 +588,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
     size_t smem = 2 * sizeof(double) * (size_t)(M - 1) * (M - 1);
+    CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, di, ctx->d_status);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -600,7 +600,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     memset(&pd, 0, sizeof(pd));
     pd.z = dz; pd.w = dw; pd.chol = dc; pd.ainv = di; pd.S = S;
     pd.S_pad = (S + 31) / 32 * 32;
-    if (M == ctx->G && ctx->fitted && ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->N <= dks::shared_path::MAXN) {
+    if (M == ctx->G && ctx->fitted && ctx->act == DKS_ACT_BINARY_LOGISTIC) {
         // shared-plan fast path: Dm table for the full varying set
         float* dm = nullptr;
         CUDA_TRY(cudaMalloc((void**)&dm, sizeof(float) * (size_t)ctx->N * pd.S_pad));

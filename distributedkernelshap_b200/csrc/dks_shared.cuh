@@ -46,6 +46,7 @@ struct SharedParams {
     const int* list;         // instances on this path
     const int* count;        // their number (device)
     float2* sums;            // [n][S_pad] (sum p1, sum p0)
+    int accumulate;          // add to sums instead of overwriting them (second and later background chunks)
 };
 
 // Two sigmoids with one reciprocal.  With ua = 2^ta, ub = 2^tb:  (1+ua)(1+ub) = 1 + sm + q,  sm = ua + ub, q = ua*ub
@@ -151,11 +152,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
         const bool risky = __any_sync(0xffffffffu, A * dmax > 1.0e18f);
         if (risky) row_sums<true, NTAIL>(dm, A, nfull, s1, s0);
         else row_sums<false, NTAIL>(dm, A, nfull, s1, s0);
-        if (s < p.S) p.sums[(size_t)i * p.S_pad + s] = make_float2(s1, s0);
+        if (s < p.S) {
+            float2* dst = p.sums + (size_t)i * p.S_pad + s;
+            if (p.accumulate) { const float2 o = *dst; s1 += o.x; s0 += o.y; }
+            *dst = make_float2(s1, s0);
+        }
     }
 }
 
-inline void launch_explain_shared(const SharedParams& p, int grid, cudaStream_t stream) {
+inline void launch_explain_shared_chunk(const SharedParams& p, int grid, cudaStream_t stream) {
     const int threads = 32 * WARPS_PER_CTA;
     switch (p.N % 16) {
 #define DKS_CASE(T) case T: explain_shared_kernel<T><<<grid, threads, 0, stream>>>(p); break;
@@ -163,6 +168,20 @@ inline void launch_explain_shared(const SharedParams& p, int grid, cudaStream_t 
         DKS_CASE(8) DKS_CASE(9) DKS_CASE(10) DKS_CASE(11) DKS_CASE(12) DKS_CASE(13) DKS_CASE(14) DKS_CASE(15)
 #undef DKS_CASE
     }
+}
+
+// Backgrounds larger than MAXN rows go through in chunks of MAXN columns of Dm (one launch each, sums accumulated)
+inline int launch_explain_shared(SharedParams p, int grid, cudaStream_t stream) {
+    const int N = p.N;
+    const float* dm = p.DmT;
+    int launches = 0;
+    for (int j0 = 0; j0 < N; j0 += MAXN, ++launches) {
+        p.N = N - j0 < MAXN ? N - j0 : MAXN;
+        p.DmT = dm + (size_t)j0 * p.S_pad;
+        p.accumulate = j0 > 0;
+        launch_explain_shared_chunk(p, grid, stream);
+    }
+    return launches;
 }
 
 struct WlsSharedParams {

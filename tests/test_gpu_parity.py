@@ -332,6 +332,44 @@ def test_config2_shape_64_features_bg512():
         eng.shap_values(d["X_explain"], nsamples=4096)
 
 
+def test_config2_shape_shared_plan():
+    """configs[2] shape with the engine's own shared plan (M = 64: the plan's 63 x 63 normal matrix is factored on the
+    device at upload) against the oracle fed that plan."""
+    from distributedkernelshap_b200.datasets import dense_tabular
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from distributedkernelshap_b200.plan import build_plan
+    from oracle.shap_kernel_oracle import KernelExplainerOracle
+    d = dense_tabular(n=4, n_features=64, n_background=512, seed=1)
+    orc = KernelExplainerOracle(d["predictor"].predict_proba, d["background"], link="logit")
+    np.random.seed(5)
+    eng = GpuKernelExplainer(d["predictor"].predict_proba, d["background"], link="logit")
+    got = eng.shap_values(d["X_explain"], nsamples=4096, l1_reg=False)
+    np.random.seed(5)
+    plan = build_plan(64, 4096)
+    for i in range(4):
+        phi = orc.explain(d["X_explain"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=4096, l1_reg=False)
+        for c in range(2):
+            assert rel_err(got[c][i], phi[:, c]) < TOL
+
+
+@pytest.mark.parametrize("N", [129, 300])
+def test_shared_fast_path_with_backgrounds_larger_than_one_chunk(N):
+    """The shared-plan fast path keeps 128 columns of Dm in registers; larger backgrounds go through in chunks whose
+    (sum p1, sum p0) are accumulated."""
+    from distributedkernelshap_b200.plan import build_plan
+    prob = make_problem(seed=31, n=9, N=N, widths=(1, 2, 1, 1, 3, 1, 1, 2, 1))
+    orc = _oracle(prob)
+    np.random.seed(3)
+    eng = _engine(prob, kernel="shared")
+    got = eng.shap_values(prob["X"], nsamples=200, l1_reg=False)
+    np.random.seed(3)
+    plan = build_plan(9, 200)
+    for i in range(prob["X"].shape[0]):
+        phi = orc.explain(prob["X"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=200, l1_reg=False)
+        for c in range(2):
+            assert rel_err(got[c][i], phi[:, c]) < TOL
+
+
 def test_large_input_is_chunked(monkeypatch):
     """Inputs above MAX_ROWS_PER_CALL are explained in row chunks with identical results."""
     from distributedkernelshap_b200 import engine as engine_mod
