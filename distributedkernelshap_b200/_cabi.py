@@ -61,6 +61,7 @@ SIGNATURES = {
     "dks_prepare_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dks_prepare_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dks_get_m_histogram": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dks_get_link_fx": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dks_get_varying": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dks_explain_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dks_explain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

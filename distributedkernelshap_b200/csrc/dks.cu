@@ -741,6 +741,16 @@ int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host) {
     return DKS_OK;
 }
 
+int dks_get_link_fx(dks_ctx* ctx, double* out_host) {
+    BIND(ctx);
+    REQUIRE(ctx->prepared && out_host, "dks_get_link_fx: call dks_prepare_* / dks_explain_* first");
+    const size_t cnt = (size_t)ctx->cur_n * ctx->C;
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_dlink, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < cnt; ++i) out_host[i] += ctx->h_linkfnull[i % ctx->C];   // stage 1 keeps link(f(x)) - link(fnull)
+    return DKS_OK;
+}
+
 int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev, const double* ext_w_dev, int ext_stride) {
     BIND(ctx);
     REQUIRE(phi_dev, "dks_explain_dev: phi is NULL");

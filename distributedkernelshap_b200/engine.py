@@ -225,18 +225,22 @@ class GpuKernelExplainer:
         need_hist = self._l1_guard(l1_reg, nsamples)
 
         if n > MAX_ROWS_PER_CALL:     # large inputs go through in row chunks (results are independent per row)
-            parts = []
+            parts, fx_parts = [], []
             for lo in range(0, n, MAX_ROWS_PER_CALL):
                 hi = min(n, lo + MAX_ROWS_PER_CALL)
                 sub = dict(nsamples=nsamples, l1_reg=l1_reg, row_offset=row_offset + lo)
                 if plans is not None:
                     sub["plans"] = plans[lo:hi]
                 part = self.shap_values(X[lo:hi], **sub)
+                fx_parts.append(self.link_predictions().reshape(hi - lo, -1))
                 parts.append(part if isinstance(part, list) else [part])
             merged = [np.concatenate([pt[c] for pt in parts], axis=0) for c in range(len(parts[0]))]
+            self._link_fx_parts = fx_parts
+            self._last_rows = n
             return merged if self.vector_out else merged[0]
 
         phi = np.zeros((self.D, n, G))
+        self._link_fx_parts = []
         if self.plan_mode == "per_instance":
             # the device draws each row's plan from (seed, global row index): tell it where this block starts
             _cabi.check(self.lib.dks_set_row_offset(self._ctx, row_offset))
@@ -260,11 +264,23 @@ class GpuKernelExplainer:
                 rc = self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), None, None, 0)
             _cabi.check(rc)
 
+        self._last_rows = n
         if not self.vector_out:
             return phi[0, 0] if single else phi[0]
         if single:
             return [phi[c, 0] for c in range(self.D)]
         return [phi[c] for c in range(self.D)]
+
+    def link_predictions(self):
+        """``link(f(x))`` of the rows of the last ``shap_values`` call, ``[n, C]`` (``[n]`` for scalar-output models):
+        stage 1 of the explain call computes it on the device, so ``KernelShap.build_explanation`` does not have to run
+        the predictor over ``X`` again for ``raw_prediction`` (kernel_shap.py:949)."""
+        if self._link_fx_parts:                 # the call went through in row chunks
+            out = np.concatenate(self._link_fx_parts, axis=0)
+        else:
+            out = np.zeros((self._last_rows, self.D))
+            _cabi.check(self.lib.dks_get_link_fx(self._ctx, _cabi.ptr(out)))
+        return out if self.vector_out else out[:, 0]
 
     def instance_plans(self):
         """Plans the device drew in the last ``plan_mode='per_instance'`` call: ``(zbits uint64[n, stride],

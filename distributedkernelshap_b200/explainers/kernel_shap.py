@@ -425,10 +425,14 @@ class KernelShap(Explainer, FitMixin):
         if isinstance(expected_value, float):
             expected_value = [expected_value]
 
+        # link(f(x)) was computed on the device by the explain call; the distributed explainer does not gather it
+        getter = None if self.distribute else getattr(self._explainer, 'link_predictions', None)
+        link_fx = getter() if getter is not None else None
         return self.build_explanation(
             X,
             shap_values,
             expected_value,
+            link_predictions=link_fx,
             summarise_result=summarise_result,
             cat_vars_start_idx=cat_vars_start_idx,
             cat_vars_enc_dim=cat_vars_enc_dim,
@@ -446,7 +450,9 @@ class KernelShap(Explainer, FitMixin):
 
         # raw predictions on the scale the explainer works in (the reference wraps link.f in np.vectorize, an
         # interpreted per-element loop; both links are NumPy ufunc expressions, so they are applied to the array)
-        raw_predictions = convert_to_link(self.link).f(np.asarray(self.predictor(X), dtype=np.float64))
+        raw_predictions = kwargs.get('link_predictions')
+        if raw_predictions is None:
+            raw_predictions = convert_to_link(self.link).f(np.asarray(self.predictor(X), dtype=np.float64))
 
         argmax_pred = np.argmax(np.atleast_2d(raw_predictions), axis=1) if self.task != 'regression' else []
         importances = rank_by_importance(shap_values, feature_names=self.feature_names)

@@ -30,3 +30,13 @@ print("engine.get_explanation(pinned numpy): %.1f us" % timeit(lambda: eng.get_e
 print("engine.get_explanation(numpy)       : %.1f us" % timeit(lambda: eng.get_explanation(X, nsamples=2048, l1_reg=False, silent=True)))
 print("KernelShap.explain (full API)       : %.1f us" % timeit(lambda: ks.explain(X, nsamples=2048, l1_reg=False, silent=True), reps=50))
 print("device timings of last call (ms):", eng.last_timings_ms())
+
+import cProfile, pstats, io
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(50):
+    ks.explain(X, nsamples=2048, l1_reg=False, silent=True)
+pr.disable()
+st = io.StringIO()
+pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(22)
+print(st.getvalue()[:4500])

@@ -210,6 +210,10 @@ def test_kernelshap_api_end_to_end():
     assert len(sv) == 2 and sv[0].shape == (40, 12)
     raw = explanation.raw["raw_prediction"]
     np.testing.assert_allclose(sv[1].sum(1) + explanation.expected_value[1], raw[:, 1], rtol=1e-7, atol=1e-7)
+    # raw_prediction comes from stage 1 of the explain call on the device: same numbers as link(predictor(X))
+    p = d["predictor"].predict_proba(d["X_explain"])
+    np.testing.assert_allclose(raw, np.log(p / (1 - p)), rtol=1e-12, atol=1e-12)
+    assert np.array_equal(explanation.raw["prediction"], p.argmax(1))
     # distributed_opts: mini-batches of 10 rows through DistributedExplainer give the same values
     dist = KernelShap(d["predictor"].predict_proba, link="logit", feature_names=d["group_names"], seed=0,
                       distributed_opts={"n_cpus": 1, "batch_size": 10, "actor_cpu_fraction": 1.0})
