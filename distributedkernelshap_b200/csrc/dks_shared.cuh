@@ -69,6 +69,30 @@ __device__ __forceinline__ void single_acc(float A, float dma, float& a1, float&
     a0 = fmaf(ua, r, a0);
 }
 
+// Packed fp32 (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per thread in one 64-bit register pair, one issue slot).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
+// Four sigmoids (two pairs, each sharing one reciprocal) in packed arithmetic: da = (dm0, dm1), db = (dm2, dm3) pair up as
+// (0,2) and (1,3).  10 packed ops + 2 MUFU per four elements (pair_acc: 11 + 1 per two).
+__device__ __forceinline__ void quad_acc(f32x2 A2, f32x2 da, f32x2 db, f32x2 one2, f32x2 two2, f32x2& a1, f32x2& a0) {
+    const f32x2 u = f2_mul(A2, da), v = f2_mul(A2, db);
+    const f32x2 q = f2_mul(u, v), sm = f2_add(u, v);
+    const f32x2 t1 = f2_add(sm, one2);
+    const f32x2 den = f2_add(q, t1);
+    float dlo, dhi;
+    f2_unpack(den, dlo, dhi);
+    const f32x2 r = f2_pack(rcp_approx(dlo), rcp_approx(dhi));
+    a1 = f2_fma(r, f2_add(t1, one2), a1);
+    a0 = f2_fma(r, f2_fma(two2, q, sm), a0);
+}
+
 // NTAIL = N % 16 (compile time): the last, partial chunk is straight-line code
 template <bool CLAMP, int NTAIL>
 __device__ __forceinline__ void row_sums(const float (&dm)[MAXN], float A, int nfull, float& s1, float& s0) {
@@ -88,6 +112,36 @@ __device__ __forceinline__ void row_sums(const float (&dm)[MAXN], float A, int n
     }
     s1 = (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]);
     s0 = (acc0[0] + acc0[1]) + (acc0[2] + acc0[3]);
+}
+
+// Same sums with packed arithmetic (the common case: no clamping needed).  dm[2j], dm[2j+1] travel as one 64-bit operand.
+template <int NTAIL>
+__device__ __forceinline__ void row_sums_packed(const float (&dm)[MAXN], float A, int nfull, float& s1, float& s0) {
+    const f32x2 A2 = f2_pack(A, A), one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
+    f32x2 acc1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, acc0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+    float t1s = 0.f, t0s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXN / 16; ++c) {
+        if (c < nfull) {
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4)
+                quad_acc(A2, f2_pack(dm[c * 16 + jj], dm[c * 16 + jj + 1]), f2_pack(dm[c * 16 + jj + 2], dm[c * 16 + jj + 3]),
+                         one2, two2, acc1[(jj >> 2) & 1], acc0[(jj >> 2) & 1]);
+        } else if (NTAIL > 0 && c == nfull) {
+#pragma unroll
+            for (int jj = 0; jj + 3 < NTAIL; jj += 4)
+                quad_acc(A2, f2_pack(dm[c * 16 + jj], dm[c * 16 + jj + 1]), f2_pack(dm[c * 16 + jj + 2], dm[c * 16 + jj + 3]),
+                         one2, two2, acc1[(jj >> 2) & 1], acc0[(jj >> 2) & 1]);
+            constexpr int Q = NTAIL & ~3;                 // what the quads covered
+            if ((NTAIL & 3) >= 2) pair_acc<false>(A, dm[c * 16 + Q], dm[c * 16 + Q + 1], t1s, t0s);
+            if (NTAIL & 1) single_acc(A, dm[c * 16 + NTAIL - 1], t1s, t0s);
+        }
+    }
+    float a, b, c2, d;
+    f2_unpack(f2_add(acc1[0], acc1[1]), a, b);
+    f2_unpack(f2_add(acc0[0], acc0[1]), c2, d);
+    s1 = (a + b) + t1s;
+    s0 = (c2 + d) + t0s;
 }
 
 // one warp = 32 coalition rows (one per lane) x a strided subset of the instances
@@ -151,7 +205,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
         // with u <= 1e18 the product q = ua*ub and the reciprocal of (1+ua)(1+ub) stay normal fp32 numbers: no clamps needed
         const bool risky = __any_sync(0xffffffffu, A * dmax > 1.0e18f);
         if (risky) row_sums<true, NTAIL>(dm, A, nfull, s1, s0);
-        else row_sums<false, NTAIL>(dm, A, nfull, s1, s0);
+        else row_sums_packed<NTAIL>(dm, A, nfull, s1, s0);
         if (s < p.S) {
             float2* dst = p.sums + (size_t)i * p.S_pad + s;
             if (p.accumulate) { const float2 o = *dst; s1 += o.x; s0 += o.y; }

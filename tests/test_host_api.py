@@ -208,6 +208,25 @@ def test_distributed_explainer_pool_matches_sequential(cpu_backend):
     assert merged[0].shape == (3, 3) and distributed.kernel_shap_postprocess_fn([np.ones((2, 3)), np.ones((1, 3))]).shape == (3, 3)
 
 
+def test_distributed_explainer_sends_global_row_offsets(monkeypatch):
+    """Every mini-batch travels with the index of its first row, so that plans drawn on the device per instance depend
+    on the row and not on how the rows were split over workers."""
+    seen = []
+
+    class Recording(OracleBackedWrapper):
+        def get_explanation(self, X, **kwargs):
+            seen.append((int(kwargs.pop("row_offset")), len(X[1])))
+            return super().get_explanation(X, **kwargs)
+
+    monkeypatch.setattr(kernel_shap, "KernelExplainerWrapper", Recording)
+    monkeypatch.setattr(distributed.parallel, "visible_gpus", lambda: 2)
+    prob = make_problem(seed=34, n=23, N=8, widths=(1, 1, 2, 1, 1, 1))
+    ks = KernelShap(prob["clf"].predict_proba, link="logit", seed=0, distributed_opts={"n_cpus": 2, "batch_size": 5})
+    ks.fit(prob["bg"], group_names=prob["group_names"], groups=prob["groups"])
+    ks.explain(prob["X"], silent=True, nsamples=62, l1_reg=False)
+    assert sorted(seen) == [(0, 5), (5, 5), (10, 5), (15, 5), (20, 3)]
+
+
 def test_serving_wrappers(cpu_backend):
     from distributedkernelshap_b200.explainers.wrappers import BatchKernelShapModel, KernelShapModel
     prob = make_problem(seed=34, n=5, N=8, widths=(1, 1, 2, 1))
