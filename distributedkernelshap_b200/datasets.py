@@ -79,3 +79,26 @@ def dense_tabular(n, n_features, n_background, seed=0, dtype=np.float64):
     predictor = LinearSoftmaxClassifier(coef, intercept, multi_class="multinomial")
     return {"predictor": predictor, "X_explain": X, "background": background,
             "groups": [[i] for i in range(n_features)], "group_names": [f"f{i}" for i in range(n_features)]}
+
+
+def wide_onehot(n, n_blocks=64, block_width=16, n_background=256, seed=0):
+    """Config [3] of BASELINE.json (the grouped reading): ``n_blocks`` categorical variables one-hot
+    encoded without dropping a level (``n_blocks * block_width`` columns), one group per variable, 2-class LR."""
+    rng = np.random.default_rng(seed)
+    D = n_blocks * block_width
+
+    def draw(rows):
+        out = np.zeros((rows, D))
+        for b in range(n_blocks):
+            probs = rng.dirichlet(np.ones(block_width))
+            levels = rng.choice(block_width, size=rows, p=probs)
+            out[np.arange(rows), b * block_width + levels] = 1.0
+        return out
+
+    both = draw(n_background + n)
+    coef = rng.normal(0.0, 0.5, size=(1, D))
+    intercept = rng.normal(0.0, 1.0, size=(1,))
+    predictor = LinearSoftmaxClassifier(coef, intercept, multi_class="multinomial")
+    groups = [list(range(b * block_width, (b + 1) * block_width)) for b in range(n_blocks)]
+    return {"predictor": predictor, "X_explain": both[n_background:], "background": both[:n_background],
+            "groups": groups, "group_names": [f"var{b}" for b in range(n_blocks)]}

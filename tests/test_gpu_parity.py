@@ -356,6 +356,36 @@ def test_config2_shape_shared_plan():
             assert rel_err(got[c][i], phi[:, c]) < TOL
 
 
+def test_config3_grouped_shape_1024_onehot_columns():
+    """BASELINE configs[3] in its grouped reading (64 one-hot variables x 16 levels = 1024 columns, one group per
+    variable) at a reduced background / budget the oracle can hold in memory: shared plan and per-instance plans."""
+    from distributedkernelshap_b200.data import DenseData
+    from distributedkernelshap_b200.datasets import wide_onehot
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from distributedkernelshap_b200.plan import build_plan
+    from oracle.shap_kernel_oracle import DenseData as ODenseData, KernelExplainerOracle
+    d = wide_onehot(n=3, n_blocks=64, block_width=16, n_background=24, seed=2)
+    orc = KernelExplainerOracle(d["predictor"].predict_proba, ODenseData(d["background"], d["group_names"], d["groups"]),
+                                link="logit", record_plans=True)
+    np.random.seed(1)
+    want = orc.shap_values(d["X_explain"], nsamples=1500, l1_reg=False)
+    np.random.seed(8)
+    eng = GpuKernelExplainer(d["predictor"].predict_proba, DenseData(d["background"], d["group_names"], d["groups"]),
+                             link="logit")
+    got = eng.shap_values(d["X_explain"], nsamples=1500, l1_reg=False, plans=[(Z, w) for (_, Z, w) in orc.plans])
+    _compare(got, want)
+    shared = eng.shap_values(d["X_explain"], nsamples=1500, l1_reg=False)          # engine's own M = 64 plan
+    np.random.seed(8)
+    plan = build_plan(64, 1500)
+    Ms, _ = eng.varying(d["X_explain"])
+    for i in range(3):
+        if Ms[i] != 64:
+            continue
+        phi = orc.explain(d["X_explain"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=1500, l1_reg=False)
+        for c in range(2):
+            assert rel_err(shared[c][i], phi[:, c]) < TOL
+
+
 @pytest.mark.parametrize("N", [129, 300])
 def test_shared_fast_path_with_backgrounds_larger_than_one_chunk(N):
     """The shared-plan fast path keeps 128 columns of Dm in registers; larger backgrounds go through in chunks whose
