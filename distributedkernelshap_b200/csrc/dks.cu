@@ -111,6 +111,8 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     const double* ext_chol = nullptr;
     const double* ext_ainv = nullptr;
     int ext_fstride = 0;
+    if (ctx->G > 64 && (ext_z != nullptr || ctx->plan_mode == 1))
+        return fail(DKS_ERR_UNSUPPORTED, "more than 64 groups: only shared plans are supported (no per-instance plans)");
     if (ctx->plan_mode == 1 && ext_z == nullptr) {
         // every instance draws its own plan on the device; the explain kernels then read it like a caller-supplied one
         if (ctx->max_plan_S < 2)
@@ -227,7 +229,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         dks::shared_path::SharedParams sp;
         sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
         sp.DmT = pg.dmT; sp.z = pg.z; sp.XW = ctx->d_XW; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
-        ctx->launches += dks::shared_path::launch_explain_shared(sp, ctx->sm_count, ctx->stream) - 1;
+        ctx->launches += dks::shared_path::launch_explain_shared(sp, pg.W, ctx->sm_count, ctx->stream) - 1;
         dks::shared_path::WlsSharedParams wp;
         wp.n = n; wp.N = ctx->N; wp.G = G; wp.C = ctx->C; wp.S = S; wp.S_pad = S_pad; wp.link = ctx->link;
         wp.uniform_w = 1; wp.sums = ctx->d_sums; wp.z = pg.z; wp.w = pg.w; wp.ainv = pg.ainv; wp.dlink = ctx->d_dlink;
@@ -247,13 +249,38 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             int pgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;
             dks::shared_path::wls_pmat_kernel<<<pgrid, dks::shared_path::PMAT_THREADS, psm, ctx->stream>>>(pp);
         } else {
-            int wgrid = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;     // persistent: ~4 CTAs of 8 warps per SM
-            dks::shared_path::wls_shared_kernel<<<wgrid, dks::shared_path::WLS_THREADS, 0, ctx->stream>>>(wp);
+            const size_t wsm = dks::shared_path::wls_shared_smem(G);
+            int per_sm = (int)((size_t)ctx->max_smem_optin / (wsm + 24 * 1024));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+            int wgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;   // persistent CTAs of 8 warps
+            if (pg.W == 1) {
+                CUDA_TRY(cudaFuncSetAttribute(dks::shared_path::wls_shared_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+                dks::shared_path::wls_shared_kernel<1><<<wgrid, dks::shared_path::WLS_THREADS, wsm, ctx->stream>>>(wp);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(dks::shared_path::wls_shared_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+                dks::shared_path::wls_shared_kernel<2><<<wgrid, dks::shared_path::WLS_THREADS, wsm, ctx->stream>>>(wp);
+            }
         }
         ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
         p.list = ctx->d_idx_other;      // the general kernel below takes the remaining instances
         p.count = ctx->d_counts + 1;
+    }
+    if (G > 64) {
+        // two-word coalition rows exist on the shared-plan path only: anything left over is reported, not computed
+        if (pg.z == nullptr || pg.S != dks_effective_S(G, ctx->nsamples_req)) {
+            ctx->h_status[0] = DKS_ERR_PLAN_MISSING; ctx->h_status[1] = G;
+            return fail(DKS_ERR_PLAN_MISSING, "no shared plan for M=%d at the current nsamples", G);
+        }
+        if (!fast)
+            return fail(DKS_ERR_UNSUPPORTED, "more than 64 groups needs the shared-plan path (binary-logistic head, uniform "
+                        "background weights, kernel 'auto' or 'shared', shared plan of M=%d uploaded)", G);
+        dks::flag_unsupported_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_counts + 1, G, ctx->d_status);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+        return DKS_OK;
     }
     if (kernel == DKS_KERNEL_AUTO || kernel == DKS_KERNEL_SHARED)
         kernel = dks::tc_supported(ctx, p) ? DKS_KERNEL_TCGEN05 : DKS_KERNEL_SIMT;
@@ -402,7 +429,7 @@ int dks_set_groups(dks_ctx* ctx, const int32_t* group_offsets, const int32_t* gr
     BIND(ctx);
     REQUIRE(group_offsets && group_cols && G > 0, "dks_set_groups: need offsets, cols, G > 0");
     if (G > DKS_MAX_GROUPS)
-        return fail(DKS_ERR_UNSUPPORTED, "dks_set_groups: G=%d groups; this build handles at most %d (one 64-bit word of "
+        return fail(DKS_ERR_UNSUPPORTED, "dks_set_groups: G=%d groups; this build handles at most %d (two 64-bit words of "
                     "coalition bits per row)", G, DKS_MAX_GROUPS);
     ctx->G = G;
     ctx->h_goff.assign(group_offsets, group_offsets + G + 1);
@@ -575,21 +602,31 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_shared_plan: M=%d out of [2,%d]", M, DKS_MAX_GROUPS);
     REQUIRE(S >= 1 && zbits_host && w_host, "dks_set_shared_plan: bad arguments");
     uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr; double* di = nullptr;
+    const int W = (M + 63) / 64;                            // 64-bit words per coalition row
     const size_t S_even = ((size_t)S + 1) & ~(size_t)1;     // TMA bulk copies move 16-byte multiples
-    CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S_even));
+    CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S_even * W));
     CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S_even));
-    CUDA_TRY(cudaMemsetAsync(dz, 0, sizeof(uint64_t) * S_even, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dz, 0, sizeof(uint64_t) * S_even * W, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(double) * S_even, ctx->stream));
     CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
     CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
     ctx->plan_allocs.push_back(dz); ctx->plan_allocs.push_back(dw); ctx->plan_allocs.push_back(dc);
     ctx->plan_allocs.push_back(di);
-    CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S * W, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
-    size_t smem = 2 * sizeof(double) * (size_t)(M - 1) * (M - 1);
-    CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, di, ctx->d_status);
+    if (W == 1) {
+        size_t smem = 2 * sizeof(double) * (size_t)(M - 1) * (M - 1);
+        CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, di, ctx->d_status);
+    } else {
+        double* scratch = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(double) * (M - 1) * (M - 1)));
+        ctx->plan_allocs.push_back(scratch);
+        size_t smem = sizeof(double) * (size_t)(M - 1) * (M - 1);
+        CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dks::plan_factor_wide_kernel<<<1, 1024, smem, ctx->stream>>>(dz, dw, S, M, dc, di, scratch, ctx->d_status);
+    }
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
@@ -598,7 +635,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         return fail(DKS_ERR_NUMERIC, "dks_set_shared_plan: normal matrix of the M=%d plan is not positive definite", M);
     PlanDev pd;
     memset(&pd, 0, sizeof(pd));
-    pd.z = dz; pd.w = dw; pd.chol = dc; pd.ainv = di; pd.S = S;
+    pd.z = dz; pd.w = dw; pd.chol = dc; pd.ainv = di; pd.S = S; pd.W = W;
     pd.S_pad = (S + 31) / 32 * 32;
     if (M == ctx->G && ctx->fitted && ctx->act == DKS_ACT_BINARY_LOGISTIC) {
         // shared-plan fast path: Dm table for the full varying set
@@ -606,13 +643,13 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         CUDA_TRY(cudaMalloc((void**)&dm, sizeof(float) * (size_t)ctx->N * pd.S_pad));
         ctx->plan_allocs.push_back(dm);
         long long total = (long long)ctx->N * pd.S_pad;
-        dks::shared_path::plan_dm_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(dz, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
+        dks::shared_path::plan_dm_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(dz, W, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
                                                                                       ctx->N, ctx->G, ctx->scale, dm);
         ctx->launches += 1;
         CUDA_TRY(cudaGetLastError());
         pd.dmT = dm;
         // projection form of the solve: P = inv(E^T W E) E^T W and d = P z_L
-        if (M - 1 <= dks::shared_path::PMAT_MAXK &&
+        if (W == 1 && M - 1 <= dks::shared_path::PMAT_MAXK &&
             dks::shared_path::wls_pmat_smem(M, pd.S_pad) + 8192 <= (size_t)ctx->max_smem_optin) {
             float* pm = nullptr; double* dv = nullptr;
             CUDA_TRY(cudaMalloc((void**)&pm, sizeof(float) * (size_t)(M - 1) * pd.S_pad));
@@ -632,7 +669,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (S > ctx->max_plan_S) ctx->max_plan_S = S;
-    TRY(dks::tc_plan_changed(ctx, M));
+    if (W == 1) TRY(dks::tc_plan_changed(ctx, M));
     return DKS_OK;
 }
 

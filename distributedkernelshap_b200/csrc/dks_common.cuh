@@ -9,11 +9,11 @@
 
 #include "dks.h"
 
-#define DKS_MAX_GROUPS 64  // one 64-bit word of coalition bits per row (multi-word plans: not yet)
+#define DKS_MAX_GROUPS 128  // coalition rows: one 64-bit word up to 64 groups, two words up to 128 (shared-plan path only)
 
 // ---- device-visible plan table entry: one shared coalition plan per number of varying groups M ----------
 struct PlanDev {
-    const uint64_t* z;   // [S] coalition bits in upstream row order
+    const uint64_t* z;   // [S][W] coalition bits in upstream row order (W = 1 word up to 64 groups, 2 up to 128)
     const double* w;     // [S] kernel weights
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
     const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
@@ -22,6 +22,7 @@ struct PlanDev {
     const double* dvec;  // [(M-1)] P z_L
     int S;
     int S_pad;
+    int W;               // 64-bit words per row
 };
 
 // What the device-side sampler needs to continue a plan past its enumerated prefix (per M; plan.py: sampling_info)

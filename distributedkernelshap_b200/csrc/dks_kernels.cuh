@@ -250,14 +250,14 @@ __global__ void prep_kernel(const double* __restrict__ X, const double* __restri
     for (int li = threadIdx.x; li < ipb; li += blockDim.x) {
         const int i = i0 + li;
         if (i >= n) continue;
-        uint64_t m = 0;
+        uint64_t m = 0;                       // varying bit-mask (groups 0..63; wider problems only use the count)
+        int M = 0;
         double z[8], o[DKS_MAX_GROUPS];
         for (int r = 0; r < R; ++r) z[r] = b[r];
         for (int g = 0; g < G; ++g) {
-            if (sflag[li * G + g]) m |= (1ull << g);
+            if (sflag[li * G + g]) { if (g < 64) m |= (1ull << g); ++M; }
             for (int r = 0; r < R; ++r) z[r] += sXW[((size_t)li * G + g) * R + r];
         }
-        const int M = __popcll(m);
         vmask[i] = m;
         Mcnt[i] = M;
         atomicAdd(&hist[M], 1);
@@ -408,6 +408,62 @@ __global__ void plan_factor_kernel(const uint64_t* __restrict__ z, const double*
     __syncthreads();
     const bool ok = wls_factor_invert(A, nA, chol, ainv);
     if (!ok && threadIdx.x == 0) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
+}
+
+// ---- plans of 65..128 groups (two words per row) -----------------------------------------------------------------
+__device__ __forceinline__ bool zbit2(const uint64_t* __restrict__ row, int k) { return (row[k >> 6] >> (k & 63)) & 1ull; }
+
+// Same factorisation for two-word plans: the matrix (up to 127 x 127) lives in shared memory, the columns of the inverse
+// are solved in a global scratch buffer [nA][nA].
+__global__ void plan_factor_wide_kernel(const uint64_t* __restrict__ z, const double* __restrict__ w, int S, int M,
+                                        double* __restrict__ chol, double* __restrict__ ainv, double* __restrict__ scratch,
+                                        int* __restrict__ status) {
+    extern __shared__ double sm_d[];
+    double* A = sm_d;
+    const int nA = M - 1, L = M - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int npairs = nA * (nA + 1) / 2;
+    for (int pr = warp; pr < npairs; pr += nwarps) {
+        int k = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+        while (k * (k + 1) / 2 > pr) --k;
+        while ((k + 1) * (k + 2) / 2 <= pr) ++k;
+        const int l = pr - k * (k + 1) / 2;
+        double acc = 0;
+        for (int s = lane; s < S; s += 32) {
+            const uint64_t* row = z + (size_t)s * 2;
+            const bool zl = zbit2(row, L);
+            if ((zbit2(row, k) != zl) && (zbit2(row, l) != zl)) acc += w[s];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) { A[k * nA + l] = acc; A[l * nA + k] = acc; }
+    }
+    __syncthreads();
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < 32) { if (!wls_cholesky_warp(A, nA)) s_ok = 0; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nA * nA; idx += blockDim.x) chol[idx] = A[idx];
+    for (int c = threadIdx.x; c < nA; c += blockDim.x) {
+        double* x = scratch + (size_t)c * nA;
+        for (int r = 0; r < nA; ++r) {
+            double v = (r == c) ? 1.0 : 0.0;
+            for (int k = 0; k < r; ++k) v -= A[r * nA + k] * x[k];
+            x[r] = v / A[r * nA + r];
+        }
+        for (int r = nA - 1; r >= 0; --r) {
+            double v = x[r];
+            for (int k = r + 1; k < nA; ++k) v -= A[k * nA + r] * x[k];
+            x[r] = v / A[r * nA + r];
+        }
+        for (int r = 0; r < nA; ++r) ainv[r * nA + c] = x[r];
+    }
+    if (threadIdx.x == 0 && !s_ok) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
+}
+
+// an instance list that must be empty (shapes no kernel covers): report instead of computing
+__global__ void flag_unsupported_kernel(const int* __restrict__ count, int detail, int* __restrict__ status) {
+    if (*count > 0 && atomicCAS(&status[0], 0, DKS_ERR_UNSUPPORTED) == 0) status[1] = detail;
 }
 
 // normal matrix of the first `rows` rows of a plan (its enumerated prefix), unfactored: the per-instance sampler adds

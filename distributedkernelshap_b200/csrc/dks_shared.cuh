@@ -21,17 +21,17 @@ constexpr float U_CLAMP = 1.152921504606846976e18f;   // 2^60: (1 + ua)(1 + ub) 
 
 // DmT[j][s] = 2^(scale * (score_j - sum_k z_sk BW[j][k]))  for the full varying set (k = group index), float32,
 // transposed so that consecutive coalitions are contiguous (coalesced row loads by lanes)
-__global__ void plan_dm_kernel(const uint64_t* __restrict__ z, int S, int S_pad, const double* __restrict__ BW,
+__global__ void plan_dm_kernel(const uint64_t* __restrict__ z, int W, int S, int S_pad, const double* __restrict__ BW,
                                const double* __restrict__ scores, int N, int G, double scale, float* __restrict__ DmT) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * S_pad) return;
     const int j = idx / S_pad, s = idx - j * S_pad;
     float out = 0.f;
     if (s < S) {
-        const uint64_t zz = z[s];
+        const uint64_t* zz = z + (size_t)s * W;
         double c = 0.0;
         for (int k = 0; k < G; ++k)
-            if ((zz >> k) & 1ull) c += BW[(size_t)j * G + k];
+            if ((zz[k >> 6] >> (k & 63)) & 1ull) c += BW[(size_t)j * G + k];
         out = (float)exp2(scale * (scores[j] - c));
     }
     DmT[idx] = out;
@@ -41,7 +41,7 @@ struct SharedParams {
     int n, N, G, S, S_pad;
     double scale;
     const float* DmT;        // [N][S_pad]
-    const uint64_t* z;       // [S]
+    const uint64_t* z;       // [S][W]
     const double* XW;        // [n][G]
     const int* list;         // instances on this path
     const int* count;        // their number (device)
@@ -145,7 +145,8 @@ __device__ __forceinline__ void row_sums_packed(const float (&dm)[MAXN], float A
 }
 
 // one warp = 32 coalition rows (one per lane) x a strided subset of the instances
-template <int NTAIL>
+// W = 64-bit words per coalition row (1: up to 64 groups, 2: up to 128)
+template <int NTAIL, int W>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(SharedParams p) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -172,30 +173,35 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
             }
         }
     }
-    const uint64_t zz = s < p.S ? p.z[s] : 0ull;
+    uint64_t zz[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
     const int nfull = N / 16;
 
-    // lanes k and k+32 hold XW_i[k], XW_i[k+32] of the NEXT instance (coalesced load, one iteration ahead)
-    double xw_lo = 0.0, xw_hi = 0.0;
+    // lane k holds XW_i[k], XW_i[k+32], ... of the NEXT instance (coalesced loads, one iteration ahead)
+    double xw[2 * W];
     int i_next = part < cnt ? p.list[part] : -1;
-    if (i_next >= 0) {
-        if (lane < G) xw_lo = p.XW[(size_t)i_next * G + lane];
-        if (lane + 32 < G) xw_hi = p.XW[(size_t)i_next * G + lane + 32];
-    }
+#pragma unroll
+    for (int q = 0; q < 2 * W; ++q) xw[q] = (i_next >= 0 && lane + 32 * q < G) ? p.XW[(size_t)i_next * G + lane + 32 * q] : 0.0;
     for (int m = part; m < cnt; m += nparts) {
         const int i = i_next;
-        const double cur_lo = xw_lo, cur_hi = xw_hi;
+        double cur[2 * W];
+#pragma unroll
+        for (int q = 0; q < 2 * W; ++q) cur[q] = xw[q];
         i_next = m + nparts < cnt ? p.list[m + nparts] : -1;
-        if (i_next >= 0) {
-            if (lane < G) xw_lo = p.XW[(size_t)i_next * G + lane];
-            if (lane + 32 < G) xw_hi = p.XW[(size_t)i_next * G + lane + 32];
-        }
+#pragma unroll
+        for (int q = 0; q < 2 * W; ++q)
+            xw[q] = (i_next >= 0 && lane + 32 * q < G) ? p.XW[(size_t)i_next * G + lane + 32 * q] : 0.0;
         // a = scale * sum_k z_k XW_i[k] in float64; A = 2^a = 2^n * 2^f with n = rint(a), |f| <= 1/2 (f exact in fp32
         // to 3e-8, ex2.approx to ~1e-7 relative)
         double a = 0.0;
-        for (int k = 0; k < G; ++k) {
-            const double xk = __shfl_sync(0xffffffffu, k < 32 ? cur_lo : cur_hi, k & 31);
-            if ((zz >> k) & 1ull) a += xk;
+#pragma unroll
+        for (int q = 0; q < 2 * W; ++q) {
+            const uint32_t zb = (uint32_t)(zz[q >> 1] >> ((q & 1) * 32));
+            for (int kk = 0; kk < 32 && 32 * q + kk < G; ++kk) {
+                const double xk = __shfl_sync(0xffffffffu, cur[q], kk);
+                if ((zb >> kk) & 1u) a += xk;
+            }
         }
         a *= p.scale;
         a = fmin(fmax(a, -120.0), 120.0);
@@ -214,10 +220,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
     }
 }
 
-inline void launch_explain_shared_chunk(const SharedParams& p, int grid, cudaStream_t stream) {
+inline void launch_explain_shared_chunk(const SharedParams& p, int words, int grid, cudaStream_t stream) {
     const int threads = 32 * WARPS_PER_CTA;
     switch (p.N % 16) {
-#define DKS_CASE(T) case T: explain_shared_kernel<T><<<grid, threads, 0, stream>>>(p); break;
+#define DKS_CASE(T)                                                             \
+    case T:                                                                     \
+        if (words == 1) explain_shared_kernel<T, 1><<<grid, threads, 0, stream>>>(p); \
+        else explain_shared_kernel<T, 2><<<grid, threads, 0, stream>>>(p);      \
+        break;
         DKS_CASE(0) DKS_CASE(1) DKS_CASE(2) DKS_CASE(3) DKS_CASE(4) DKS_CASE(5) DKS_CASE(6) DKS_CASE(7)
         DKS_CASE(8) DKS_CASE(9) DKS_CASE(10) DKS_CASE(11) DKS_CASE(12) DKS_CASE(13) DKS_CASE(14) DKS_CASE(15)
 #undef DKS_CASE
@@ -225,7 +235,7 @@ inline void launch_explain_shared_chunk(const SharedParams& p, int grid, cudaStr
 }
 
 // Backgrounds larger than MAXN rows go through in chunks of MAXN columns of Dm (one launch each, sums accumulated)
-inline int launch_explain_shared(SharedParams p, int grid, cudaStream_t stream) {
+inline int launch_explain_shared(SharedParams p, int words, int grid, cudaStream_t stream) {
     const int N = p.N;
     const float* dm = p.DmT;
     int launches = 0;
@@ -233,7 +243,7 @@ inline int launch_explain_shared(SharedParams p, int grid, cudaStream_t stream) 
         p.N = N - j0 < MAXN ? N - j0 : MAXN;
         p.DmT = dm + (size_t)j0 * p.S_pad;
         p.accumulate = j0 > 0;
-        launch_explain_shared_chunk(p, grid, stream);
+        launch_explain_shared_chunk(p, words, grid, stream);
     }
     return launches;
 }
@@ -378,10 +388,12 @@ __global__ void __launch_bounds__(PMAT_THREADS) wls_pmat_kernel(WlsPmatParams p)
 // Persistent CTAs of 8 warps, each looping over instances: y = link(ey) - link(fnull) per coalition, E^T W y in 2^-40
 // fixed point (integer adds: exact, order-independent), beta = inv(E^T W E) (E^T W y), phi.
 constexpr int WLS_THREADS = 256;
+inline size_t wls_shared_smem(int G) { return sizeof(double) * (size_t)(G - 1) * (G - 1); }
+template <int W>
 __global__ void __launch_bounds__(WLS_THREADS) wls_shared_kernel(WlsSharedParams p) {
-    __shared__ double s_ainv[63 * 63];
-    __shared__ long long s_part[WLS_THREADS / 32][64];
-    __shared__ double s_rhs[64];
+    extern __shared__ double s_ainv[];                   // [(G-1)][(G-1)]
+    __shared__ long long s_part[WLS_THREADS / 32][64 * W];
+    __shared__ double s_rhs[64 * W];
     __shared__ LogTabEntry s_logtab[DKS_LOGTAB_SIZE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int G = p.G, nA = G - 1, L = G - 1;
@@ -407,10 +419,11 @@ __global__ void __launch_bounds__(WLS_THREADS) wls_shared_kernel(WlsSharedParams
                 double y;
                 if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(a.x, a.y, s_logtab) - lf1;
                 else y = (p.uniform_w ? (double)a.x * inv_n : (double)a.x) - f1;
-                const uint64_t zrow = p.z[s];
-                const bool zl = (zrow >> L) & 1ull;
+                const uint64_t* zrow = p.z + (size_t)s * W;
+                const bool zl = (zrow[L >> 6] >> (L & 63)) & 1ull;
                 const double v = p.w[s] * (y - (zl ? delta : 0.0));
-                const uint32_t zb = (uint32_t)((zl ? ~zrow : zrow) >> k0);
+                const uint64_t zw = zrow[k0 >> 6];               // a 16-bit window never straddles two words
+                const uint32_t zb = (uint32_t)((zl ? ~zw : zw) >> (k0 & 63));
                 const long long vi = zl ? -to_fix(v) : to_fix(v);
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
@@ -434,9 +447,11 @@ __global__ void __launch_bounds__(WLS_THREADS) wls_shared_kernel(WlsSharedParams
         __syncthreads();
         if (wib == 0) {
             double sum = 0.0;
-            double beta[2] = {0.0, 0.0};
+            double beta[2 * W];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 2 * W; ++h) beta[h] = 0.0;
+#pragma unroll
+            for (int h = 0; h < 2 * W; ++h) {
                 const int k = lane + 32 * h;
                 if (k < nA) {
                     double b0 = 0.0, b1 = 0.0;      // two chains: the dot product is latency bound otherwise
@@ -452,7 +467,7 @@ __global__ void __launch_bounds__(WLS_THREADS) wls_shared_kernel(WlsSharedParams
             }
             sum = warp_sum(sum);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 2 * W; ++h) {
                 const int k = lane + 32 * h;
                 if (k < G) {
                     double val = k < nA ? beta[h] : delta - sum;       // the eliminated (last) group takes the remainder

@@ -245,6 +245,9 @@ class GpuKernelExplainer:
             # the device draws each row's plan from (seed, global row index): tell it where this block starts
             _cabi.check(self.lib.dks_set_row_offset(self._ctx, row_offset))
         if plans is not None:
+            if G > 64:
+                raise NotImplementedError("caller-supplied per-instance plans need at most 64 groups (two-word coalition "
+                                          "rows exist on the shared-plan path only)")
             zb, w, stride = self._pack_external_plans(plans, n, nsamples)
             if need_hist:
                 _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), n))

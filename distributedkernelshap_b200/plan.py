@@ -14,7 +14,7 @@ from math import comb
 
 import numpy as np
 
-MAX_GROUPS = 64
+MAX_GROUPS = 128          # coalition rows are one 64-bit word up to 64 varying groups, two words up to 128
 
 
 def resolve_nsamples(M, nsamples="auto"):
@@ -52,8 +52,14 @@ def _combination_bits(M, size):
     return out
 
 
+def mask_words(M):
+    """64-bit words per coalition row."""
+    return (M + 63) // 64
+
+
 class CoalitionPlan:
-    """``zbits`` uint64[S], ``weights`` float64[S] in upstream row order, plus bookkeeping."""
+    """``zbits`` uint64[S] (M <= 64) or uint64[S, 2] (little-endian words, 64 < M <= 128), ``weights`` float64[S] in
+    upstream row order, plus bookkeeping."""
 
     def __init__(self, M, zbits, weights, nfixed, num_full_subsets, weight_left):
         self.M = M
@@ -69,8 +75,9 @@ class CoalitionPlan:
 
     def dense(self):
         """[S, M] 0/1 matrix (upstream's ``maskMatrix``)."""
-        k = np.arange(self.M, dtype=np.uint64)
-        return ((self.zbits[:, None] >> k[None, :]) & np.uint64(1)).astype(np.uint8)
+        words = self.zbits.reshape(len(self.zbits), -1)
+        k = np.arange(self.M)
+        return ((words[:, k // 64] >> (k % 64).astype(np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
 
 
 def build_plan(M, nsamples="auto", rng=None):
@@ -80,6 +87,8 @@ def build_plan(M, nsamples="auto", rng=None):
         raise ValueError(f"plans need 2 <= M <= {MAX_GROUPS} (got {M})")
     if rng is None:
         rng = np.random
+    if M > 64:
+        return _build_plan_wide(M, nsamples, rng)
     S, _ = resolve_nsamples(M, nsamples)
     full_mask = (1 << M) - 1
     wv, n_sizes, n_paired = size_weights(M)
@@ -157,6 +166,79 @@ def build_plan(M, nsamples="auto", rng=None):
     return CoalitionPlan(M, zbits, weights, nfixed, n_full, weight_left)
 
 
+def _build_plan_wide(M, nsamples, rng):
+    """Same rule for 64 < M <= 128, with Python integers as masks (two 64-bit words per row on the way out)."""
+    from itertools import combinations
+    S, _ = resolve_nsamples(M, nsamples)
+    full_mask = (1 << M) - 1
+    wv, n_sizes, n_paired = size_weights(M)
+    rows, weights = [], []
+    n_full, budget, rem = 0, S, wv.copy()
+    for size in range(1, n_sizes + 1):
+        paired = size <= n_paired
+        n_sub = float(comb(M, size)) * (2 if paired else 1)
+        if budget * rem[size - 1] / n_sub < 1.0 - 1e-8:
+            break
+        n_full += 1
+        budget -= n_sub
+        if rem[size - 1] < 1.0:
+            rem /= (1 - rem[size - 1])
+        w_row = wv[size - 1] / comb(M, size) / (2.0 if paired else 1.0)
+        for inds in combinations(range(M), size):
+            word = 0
+            for k in inds:
+                word |= 1 << k
+            rows.append(word)
+            weights.append(w_row)
+            if paired:
+                rows.append(word ^ full_mask)
+                weights.append(w_row)
+    nfixed = len(rows)
+    weight_left = 0.0
+    if n_full != n_sizes:
+        left = S - nfixed
+        p = wv.copy()
+        p[:n_paired] /= 2
+        p = p[n_full:]
+        p /= p.sum()
+        picks = rng.choice(len(p), 4 * left, p=p)
+        first_row, pos = {}, 0
+        while left > 0 and pos < len(picks):
+            size = int(picks[pos]) + n_full + 1
+            pos += 1
+            word = 0
+            for k in rng.permutation(M)[:size]:
+                word |= 1 << int(k)
+            row = first_row.get(word)
+            fresh = row is None
+            if fresh:
+                first_row[word] = len(rows)
+                rows.append(word)
+                weights.append(1.0)
+                left -= 1
+            else:
+                weights[row] += 1.0
+            if left > 0 and size <= n_paired:
+                if fresh:
+                    rows.append(word ^ full_mask)
+                    weights.append(1.0)
+                    left -= 1
+                else:
+                    weights[row + 1] += 1.0
+        weight_left = float(wv[n_full:].sum())
+        wts = np.array(weights)
+        wts[nfixed:] *= weight_left / wts[nfixed:].sum()
+        weights = list(wts)
+    zbits = np.zeros((S, 2), dtype=np.uint64)
+    wout = np.zeros(S)
+    lo64 = (1 << 64) - 1
+    for r, word in enumerate(rows):
+        zbits[r, 0] = word & lo64
+        zbits[r, 1] = word >> 64
+    wout[:len(weights)] = weights
+    return CoalitionPlan(M, zbits, wout, nfixed, n_full, weight_left)
+
+
 def sampling_info(plan):
     """What the device-side sampler (csrc/dks_sampler.cuh, ``dks_set_plan_sampling``) needs to continue a plan past its
     enumerated prefix: ``(nfixed, n_full, n_paired, cdf float64[ncdf], weight_left)``.  ``cdf`` is the cumulative
@@ -176,10 +258,16 @@ def sampling_info(plan):
 
 
 def pack_dense_plan(Z):
-    """[S, M] 0/1 matrix -> uint64[S] bit words (for feeding externally built plans to the engine)."""
+    """[S, M] 0/1 matrix -> uint64[S] bit words, or uint64[S, 2] for 64 < M <= 128 (for feeding externally built plans
+    to the engine and for comparing plans in tests)."""
     Z = np.asarray(Z)
     S, M = Z.shape
     if M > MAX_GROUPS:
-        raise ValueError(f"at most {MAX_GROUPS} varying groups per coalition word")
-    k = np.arange(M, dtype=np.uint64)
-    return (Z.astype(np.uint64) << k[None, :]).sum(axis=1, dtype=np.uint64)
+        raise ValueError(f"at most {MAX_GROUPS} varying groups per coalition row")
+    k = np.arange(min(M, 64), dtype=np.uint64)
+    lo = (Z[:, :64].astype(np.uint64) << k[None, :]).sum(axis=1, dtype=np.uint64)
+    if M <= 64:
+        return lo
+    k2 = np.arange(M - 64, dtype=np.uint64)
+    hi = (Z[:, 64:].astype(np.uint64) << k2[None, :]).sum(axis=1, dtype=np.uint64)
+    return np.stack([lo, hi], axis=1)

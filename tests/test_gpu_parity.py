@@ -449,3 +449,37 @@ def test_multiclass_softmax_head(link):
     fx = clf.predict_proba(X)
     for c in range(C):
         np.testing.assert_allclose(got[c].sum(1), orc.link.f(fx[:, c]) - eng.expected_value[c], rtol=1e-7, atol=1e-8)
+
+
+def test_two_word_coalition_rows_up_to_128_groups():
+    """65..128 groups (BASELINE configs[4] has 128 ungrouped features): coalition rows take two 64-bit words; supported
+    on the shared-plan path.  GPU against the oracle fed the engine's plan, at a size the oracle holds in memory."""
+    from distributedkernelshap_b200.datasets import dense_tabular
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    from distributedkernelshap_b200.plan import build_plan
+    from oracle.shap_kernel_oracle import KernelExplainerOracle
+    for G, N, ns, seed in [(128, 40, 1500, 0), (70, 33, 600, 1)]:
+        d = dense_tabular(n=3, n_features=G, n_background=N, seed=seed)
+        orc = KernelExplainerOracle(d["predictor"].predict_proba, d["background"], link="logit")
+        np.random.seed(11)
+        eng = GpuKernelExplainer(d["predictor"].predict_proba, d["background"], link="logit")
+        got = eng.shap_values(d["X_explain"], nsamples=ns, l1_reg=False)
+        np.random.seed(11)
+        plan = build_plan(G, ns)
+        assert plan.zbits.shape == (ns, 2)
+        for i in range(3):
+            phi = orc.explain(d["X_explain"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=ns, l1_reg=False)
+            for c in range(2):
+                assert rel_err(got[c][i], phi[:, c]) < TOL
+        fx = d["predictor"].predict_proba(d["X_explain"])
+        np.testing.assert_allclose(got[1].sum(1), np.log(fx[:, 1] / fx[:, 0]) - eng.expected_value[1], rtol=1e-8, atol=1e-8)
+    # what the two-word path does not cover is refused, not approximated
+    d = dense_tabular(n=2, n_features=80, n_background=8, seed=3)
+    X = d["X_explain"].copy()
+    X[0, 5] = d["background"][0, 5]
+    d["background"][:, 5] = d["background"][0, 5]          # group 5 does not vary for instance 0: partial varying set
+    eng = GpuKernelExplainer(d["predictor"].predict_proba, d["background"], link="logit")
+    with pytest.raises(Exception, match="status 3|UNSUPPORTED|unsupported|more than 64"):
+        eng.shap_values(X, nsamples=300, l1_reg=False)
+    with pytest.raises(NotImplementedError):
+        eng.shap_values(X[1:], nsamples=300, l1_reg=False, plans=[None])

@@ -37,7 +37,7 @@ def test_plan_rejects_unsupported_sizes():
     with pytest.raises(ValueError):
         build_plan(1)
     with pytest.raises(ValueError):
-        build_plan(65)
+        build_plan(129)
 
 
 def test_sampling_info_and_philox_stream_adapter():
@@ -63,3 +63,19 @@ def test_sampling_info_and_philox_stream_adapter():
         assert abs(weight_left - info["weight_left"]) < 1e-15
     full = build_plan(5, 1000)
     assert len(sampling_info(full)[3]) == 0
+
+
+def test_wide_plans_two_words_match_the_oracle():
+    from oracle.shap_kernel_oracle import build_plan as oracle_build_plan
+    from distributedkernelshap_b200.plan import build_plan, pack_dense_plan
+    for M, ns in [(65, 400), (100, 700), (128, "auto")]:
+        np.random.seed(4)
+        plan = build_plan(M, ns)
+        np.random.seed(4)
+        Z, w, info = oracle_build_plan(M, plan.S)
+        assert plan.zbits.shape == (plan.S, 2) and plan.nfixed == info["nfixed"]
+        np.testing.assert_array_equal(plan.zbits, pack_dense_plan(Z))
+        np.testing.assert_array_equal(plan.dense(), Z)
+        np.testing.assert_allclose(plan.weights, w, rtol=1e-14)
+    with pytest.raises(ValueError):
+        build_plan(129, 100)
