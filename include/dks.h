@@ -91,7 +91,8 @@ int dks_predict_host(dks_ctx* ctx, const double* X_host, int n, double* out_host
 int dks_set_nsamples(dks_ctx* ctx, int nsamples);
 /* S an instance with M varying groups evaluates under the current request (upstream rule). */
 int dks_effective_nsamples(dks_ctx* ctx, int M, int* S);
-/* one plan shared by every instance with M varying groups: zbits [S] (bit k = k-th varying group present),
+/* one plan shared by every instance with M varying groups: zbits [S][W] little-endian 64-bit words, W = 1 for M <= 64 and
+ * 2 for 64 < M <= 128 (bit k = k-th varying group present; two-word rows are evaluated by the shared-plan path only),
  * w [S] kernel weights, in upstream row order.  Copies to the device and factors the normal matrix. */
 int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, const double* w_host);
 int dks_clear_plans(dks_ctx* ctx);
