@@ -29,9 +29,11 @@ def _expected_plan(M, nsamples, seed, row):
     ((1, 2, 1, 3, 1, 1), 40),                          # M = 6: 62 coalitions in all -> duplicates on most draws
     ((1,) * 9, 120),                                   # M = 9 (odd: every size is paired)
     ((1,) * 20, "auto"),                               # M = 20, 2088 rows
+    ((1,) * 40, 1500),                                 # M = 40: subsets of up to 20 members (several Philox blocks per draw)
+    ((1,) * 64, 4096),                                 # M = 64 (all 64 bits of the word in use), 3968 sampled rows
 ])
 def test_device_plans_equal_the_sequential_loop_on_the_same_stream(widths, nsamples):
-    prob = make_problem(seed=21, n=12, N=10, widths=widths)
+    prob = make_problem(seed=21, n=12 if len(widths) < 40 else 4, N=10, widths=widths)
     eng = _engine(prob, kernel="simt", seed=77, plan_mode="per_instance")
     orc = _oracle(prob)
     got = eng.shap_values(prob["X"], nsamples=nsamples, l1_reg=False)
