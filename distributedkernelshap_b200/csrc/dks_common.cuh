@@ -140,6 +140,7 @@ struct dks_ctx {
     size_t cap_X = 0;
     const double* cur_X = nullptr;
     double* d_XW = nullptr;
+    double* d_XT = nullptr;      // [n][ceil(G/4)][16] nibble tables of the scaled grouped contributions (binary head)
     unsigned char* d_vflag = nullptr;
     uint64_t* d_vmask = nullptr;
     int* d_M = nullptr;

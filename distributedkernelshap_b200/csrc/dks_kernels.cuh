@@ -216,7 +216,8 @@ __global__ void prep_kernel(const double* __restrict__ X, const double* __restri
                             const double* __restrict__ linkfnull, int n, int N, int D, int G, int R, int C, int act,
                             double kappa, int link, int ipb, double* __restrict__ XW, uint64_t* __restrict__ vmask,
                             int* __restrict__ Mcnt, double* __restrict__ dlink, int* __restrict__ hist,
-                            int* __restrict__ counts, int* __restrict__ idx_full, int* __restrict__ idx_other) {
+                            int* __restrict__ counts, int* __restrict__ idx_full, int* __restrict__ idx_other,
+                            double* __restrict__ XT, double xt_scale) {
     extern __shared__ unsigned char prep_smem[];
     double* sXW = reinterpret_cast<double*>(prep_smem);                        // [ipb][G][R]
     unsigned char* sflag = prep_smem + sizeof(double) * (size_t)ipb * G * R;   // [ipb][G]
@@ -247,6 +248,21 @@ __global__ void prep_kernel(const double* __restrict__ X, const double* __restri
         sflag[idx] = varies ? 1 : 0;
     }
     __syncthreads();
+    if (XT != nullptr) {
+        // XT[i][t][x] = xt_scale * sum_{b<4} bit_b(x) XW[i][4t+b]: the shared-plan kernel adds one table entry per nibble
+        // of a coalition row instead of one term per group (R == 1)
+        const int ntab = (G + 3) / 4;
+        for (int idx = threadIdx.x; idx < ipb * ntab * 16; idx += blockDim.x) {
+            const int li = idx / (ntab * 16), rem = idx - li * ntab * 16, t = rem >> 4, x = rem & 15;
+            const int i = i0 + li;
+            if (i >= n) continue;
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (((x >> b) & 1) && 4 * t + b < G) acc += sXW[(size_t)li * G + 4 * t + b];
+            XT[((size_t)i * ntab + t) * 16 + x] = xt_scale * acc;
+        }
+    }
     for (int li = threadIdx.x; li < ipb; li += blockDim.x) {
         const int i = i0 + li;
         if (i >= n) continue;

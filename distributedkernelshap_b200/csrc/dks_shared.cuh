@@ -42,7 +42,7 @@ struct SharedParams {
     double scale;
     const float* DmT;        // [N][S_pad]
     const uint64_t* z;       // [S][W]
-    const double* XW;        // [n][G]
+    const double* XT;        // [n][ceil(G/4)][16] nibble tables: scale * sum of the contributions a nibble selects
     const int* list;         // instances on this path
     const int* count;        // their number (device)
     float2* sums;            // [n][S_pad] (sum p1, sum p0)
@@ -178,32 +178,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
     for (int w = 0; w < W; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
     const int nfull = N / 16;
 
-    // lane k holds XW_i[k], XW_i[k+32], ... of the NEXT instance (coalesced loads, one iteration ahead)
-    double xw[2 * W];
-    int i_next = part < cnt ? p.list[part] : -1;
-#pragma unroll
-    for (int q = 0; q < 2 * W; ++q) xw[q] = (i_next >= 0 && lane + 32 * q < G) ? p.XW[(size_t)i_next * G + lane + 32 * q] : 0.0;
+    const int ntab = (G + 3) / 4;
     for (int m = part; m < cnt; m += nparts) {
-        const int i = i_next;
-        double cur[2 * W];
+        const int i = p.list[m];
+        // a = scale * sum_k z_k XW_i[k] in float64, one table entry per nibble of the row (prep_kernel built the tables);
+        // the loads are independent, two partial sums keep the add chain short.
+        // A = 2^a = 2^n * 2^f with n = rint(a), |f| <= 1/2 (f exact in fp32 to 3e-8, ex2.approx to ~1e-7 relative)
+        const double* xt = p.XT + (size_t)i * ntab * 16;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 2 * W; ++q) cur[q] = xw[q];
-        i_next = m + nparts < cnt ? p.list[m + nparts] : -1;
-#pragma unroll
-        for (int q = 0; q < 2 * W; ++q)
-            xw[q] = (i_next >= 0 && lane + 32 * q < G) ? p.XW[(size_t)i_next * G + lane + 32 * q] : 0.0;
-        // a = scale * sum_k z_k XW_i[k] in float64; A = 2^a = 2^n * 2^f with n = rint(a), |f| <= 1/2 (f exact in fp32
-        // to 3e-8, ex2.approx to ~1e-7 relative)
-        double a = 0.0;
-#pragma unroll
-        for (int q = 0; q < 2 * W; ++q) {
-            const uint32_t zb = (uint32_t)(zz[q >> 1] >> ((q & 1) * 32));
-            for (int kk = 0; kk < 32 && 32 * q + kk < G; ++kk) {
-                const double xk = __shfl_sync(0xffffffffu, cur[q], kk);
-                if ((zb >> kk) & 1u) a += xk;
+        for (int w = 0; w < W; ++w) {
+#pragma unroll 4
+            for (int t = 0; t < 16 && 16 * w + t < ntab; t += 2) {
+                a0 += __ldg(xt + (16 * w + t) * 16 + (int)((zz[w] >> (4 * t)) & 15ull));
+                if (16 * w + t + 1 < ntab) a1 += __ldg(xt + (16 * w + t + 1) * 16 + (int)((zz[w] >> (4 * t + 4)) & 15ull));
             }
         }
-        a *= p.scale;
+        double a = a0 + a1;
         a = fmin(fmax(a, -120.0), 120.0);
         const double an = rint(a);
         const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
