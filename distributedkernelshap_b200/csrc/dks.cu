@@ -243,13 +243,10 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             pp.sums = ctx->d_sums; pp.pmat = pg.pmat; pp.dvec = pg.dvec; pp.dlink = ctx->d_dlink;
             pp.linkfnull = ctx->d_linkfnull; pp.fnull = ctx->d_fnull; pp.list = ctx->d_idx_full; pp.count = ctx->d_counts;
             pp.phi = phi_dev;
-            size_t psm = dks::shared_path::wls_pmat_smem(G, S_pad);
-            CUDA_TRY(cudaFuncSetAttribute(dks::shared_path::wls_pmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-            int per_sm = (int)((size_t)ctx->max_smem_optin / (psm + 8192));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > 4) per_sm = 4;
-            int pgrid = n < ctx->sm_count * per_sm ? n : ctx->sm_count * per_sm;
-            dks::shared_path::wls_pmat_kernel<<<pgrid, dks::shared_path::PMAT_THREADS, psm, ctx->stream>>>(pp);
+            cudaError_t perr = cudaSuccess;
+            if (!dks::shared_path::launch_wls_pmat(pp, n, ctx->sm_count, ctx->max_smem_optin, ctx->stream, &perr))
+                return fail(DKS_ERR_UNSUPPORTED, "projection solve does not fit shared memory");
+            CUDA_TRY(perr);
         } else {
             const size_t wsm = dks::shared_path::wls_shared_smem(G);
             int per_sm = (int)((size_t)ctx->max_smem_optin / (wsm + 24 * 1024));
@@ -652,7 +649,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         pd.dmT = dm;
         // projection form of the solve: P = inv(E^T W E) E^T W and d = P z_L
         if (W == 1 && M - 1 <= dks::shared_path::PMAT_MAXK &&
-            dks::shared_path::wls_pmat_smem(M, pd.S_pad) + 8192 <= (size_t)ctx->max_smem_optin) {
+            dks::shared_path::wls_pmat_smem(M, pd.S_pad, false) + 8192 <= (size_t)ctx->max_smem_optin) {
             float* pm = nullptr; double* dv = nullptr;
             CUDA_TRY(cudaMalloc((void**)&pm, sizeof(float) * (size_t)(M - 1) * pd.S_pad));
             CUDA_TRY(cudaMalloc((void**)&dv, sizeof(double) * (M - 1)));

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "dks_kernels.cuh"
+#include "dks_tc.cuh"
 
 namespace dks {
 namespace shared_path {
@@ -211,7 +212,194 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
     }
 }
 
+// ---- the same kernel with the Dm rows parked in TENSOR MEMORY ------------------------------------------------------
+// The register version above keeps a lane's row of Dm (up to 128 floats) in registers: 168 registers per thread, 12
+// warps per SM, and the kernel is latency bound.  TMEM (512 columns x 128 lanes x 32 bit per SM) is otherwise idle on this
+// path, so it holds the rows instead: warp w owns TMEM lanes 32*(w%4) .. +31 (the hardware's lane quarter of that warp)
+// and the column range (w/4)*cstride .. +N; it writes its 32 rows once (tcgen05.st) and re-reads them 16 columns at a time
+// (tcgen05.ld, next chunk in flight while the current one is consumed).  That frees ~100 registers per thread: 16 or 20
+// warps per SM instead of 12.
+constexpr int TM_MAX_WARPS = 20;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float v0, float v1, float v2, float v3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v0)),
+                 "r"(__float_as_uint(v1)), "r"(__float_as_uint(v2)), "r"(__float_as_uint(v3))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one 16-column chunk of a row: four packed quads (or the clamped scalar pairs), NV = valid columns of this chunk
+template <bool CLAMP, int NV>
+__device__ __forceinline__ void chunk_sums(const float (&v)[16], float A, f32x2 A2, f32x2 one2, f32x2 two2, f32x2 (&acc1)[2],
+                                           f32x2 (&acc0)[2], float& t1s, float& t0s) {
+    if (!CLAMP) {
+#pragma unroll
+        for (int jj = 0; jj + 3 < NV; jj += 4)
+            quad_acc(A2, f2_pack(v[jj], v[jj + 1]), f2_pack(v[jj + 2], v[jj + 3]), one2, two2, acc1[(jj >> 2) & 1],
+                     acc0[(jj >> 2) & 1]);
+        constexpr int Q = NV & ~3;
+        if ((NV & 3) >= 2) pair_acc<false>(A, v[Q], v[Q + 1], t1s, t0s);
+        if (NV & 1) single_acc(A, v[NV - 1], t1s, t0s);
+    } else {
+#pragma unroll
+        for (int jj = 0; jj + 1 < NV; jj += 2) pair_acc<true>(A, v[jj], v[jj + 1], t1s, t0s);
+        if (NV & 1) single_acc(A, v[NV - 1], t1s, t0s);
+    }
+}
+
+template <int NTAIL, int W>
+__global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kernel(SharedParams p, int warps_used, int cstride) {
+    __shared__ uint32_t s_tmem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = s_tmem;
+
+    const int n_rg = p.S_pad / 32;                       // row groups
+    const int total_warps = gridDim.x * warps_used;
+    const int nparts = total_warps / n_rg;               // replicas of every row group
+    const int gw = blockIdx.x * warps_used + warp;
+    const bool active = warp < warps_used && nparts > 0 && gw < nparts * n_rg;
+    if (active) {
+        const int rg = gw % n_rg, part = gw / n_rg;
+        const int s = rg * 32 + lane;
+        const int cnt = *p.count;
+        const int N = p.N, G = p.G;
+        const int nfull = N / 16;
+        // this warp's slice of tensor memory: its lane quarter, column range warp / 4
+        const uint32_t taddr = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * cstride);
+        float dmax = 0.f;
+        for (int c = 0; c * 16 < N; ++c) {
+            float v[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int j = c * 16 + jj;
+                v[jj] = j < N ? p.DmT[(size_t)j * p.S_pad + s] : 0.f;
+                dmax = fmaxf(dmax, v[jj]);
+            }
+            if (c < nfull) {
+                tmem_st16(taddr + c * 16, v);
+            } else {
+                // the tail is written four columns at a time: the slice stride is N rounded up to 4, and a wider store
+                // would run into the next warp's slice
+#pragma unroll
+                for (int q = 0; q < (NTAIL + 3) / 4; ++q) tmem_st4(taddr + c * 16 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        }
+        tmem_st_wait();
+        uint64_t zz[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
+        const int ntab = (G + 3) / 4;
+        const f32x2 one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
+
+        for (int m = part; m < cnt; m += nparts) {
+            const int i = p.list[m];
+            const double* xt = p.XT + (size_t)i * ntab * 16;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+#pragma unroll 4
+                for (int t = 0; t < 16 && 16 * w + t < ntab; t += 2) {
+                    a0 += __ldg(xt + (16 * w + t) * 16 + (int)((zz[w] >> (4 * t)) & 15ull));
+                    if (16 * w + t + 1 < ntab) a1 += __ldg(xt + (16 * w + t + 1) * 16 + (int)((zz[w] >> (4 * t + 4)) & 15ull));
+                }
+            }
+            double a = a0 + a1;
+            a = fmin(fmax(a, -120.0), 120.0);
+            const double an = rint(a);
+            const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
+            const bool risky = __any_sync(0xffffffffu, A * dmax > 1.0e18f);
+            const f32x2 A2 = f2_pack(A, A);
+            f32x2 acc1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, acc0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+            float t1s = 0.f, t0s = 0.f;
+            // chunks of 16 columns, the next one in flight while this one is consumed
+            float va[16], vb[16];
+            const int nch = nfull + (NTAIL > 0 ? 1 : 0);
+            tc::tmem_ld16(taddr, va);
+            for (int c = 0; c < nch; c += 2) {
+                tc::tmem_ld_wait(va);
+                if (c + 1 < nch) tc::tmem_ld16(taddr + (c + 1) * 16, vb);
+                if (c < nfull) {
+                    if (risky) chunk_sums<true, 16>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                    else chunk_sums<false, 16>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                } else if (NTAIL > 0) {
+                    if (risky) chunk_sums<true, NTAIL>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                    else chunk_sums<false, NTAIL>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                }
+                if (c + 1 < nch) {
+                    tc::tmem_ld_wait(vb);
+                    if (c + 2 < nch) tc::tmem_ld16(taddr + (c + 2) * 16, va);
+                    if (c + 1 < nfull) {
+                        if (risky) chunk_sums<true, 16>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                        else chunk_sums<false, 16>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                    } else if (NTAIL > 0) {
+                        if (risky) chunk_sums<true, NTAIL>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                        else chunk_sums<false, NTAIL>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
+                    }
+                }
+            }
+            float q0, q1, q2, q3;
+            f2_unpack(f2_add(acc1[0], acc1[1]), q0, q1);
+            f2_unpack(f2_add(acc0[0], acc0[1]), q2, q3);
+            float s1 = (q0 + q1) + t1s, s0 = (q2 + q3) + t0s;
+            if (s < p.S) {
+                float2* dst = p.sums + (size_t)i * p.S_pad + s;
+                if (p.accumulate) { const float2 o = *dst; s1 += o.x; s0 += o.y; }
+                *dst = make_float2(s1, s0);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// 0: registers, 1: tensor memory (default); DKS_SHARED_DM=regs selects the register version for comparisons
+inline bool shared_dm_in_tmem() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("DKS_SHARED_DM");
+        mode = (e && e[0] == 'r') ? 0 : 1;
+    }
+    return mode == 1;
+}
+
 inline void launch_explain_shared_chunk(const SharedParams& p, int words, int grid, cudaStream_t stream) {
+    if (shared_dm_in_tmem()) {
+        // column stride of a warp's slice: N rounded up to 4.  Reads are whole 16-column chunks (the last one may look into
+        // the next slice, which is harmless), so the last slice must leave room for a full chunk: 5 slices up to N = 100,
+        // 4 up to N = 128
+        const int cstride = (p.N + 3) / 4 * 4;
+        const int reach = (p.N + 15) / 16 * 16;              // columns a slice's reads can touch
+        int slices = 5;
+        while (slices > 1 && (slices - 1) * cstride + reach > 512) --slices;
+        const int warps_used = 4 * slices;
+        switch (p.N % 16) {
+#define DKS_CASE(T)                                                                                          \
+    case T:                                                                                                  \
+        if (words == 1) explain_shared_tmem_kernel<T, 1><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride); \
+        else explain_shared_tmem_kernel<T, 2><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride);            \
+        break;
+            DKS_CASE(0) DKS_CASE(1) DKS_CASE(2) DKS_CASE(3) DKS_CASE(4) DKS_CASE(5) DKS_CASE(6) DKS_CASE(7)
+            DKS_CASE(8) DKS_CASE(9) DKS_CASE(10) DKS_CASE(11) DKS_CASE(12) DKS_CASE(13) DKS_CASE(14) DKS_CASE(15)
+#undef DKS_CASE
+        }
+        return;
+    }
+
     const int threads = 32 * WARPS_PER_CTA;
     switch (p.N % 16) {
 #define DKS_CASE(T)                                                             \
@@ -298,26 +486,34 @@ struct WlsPmatParams {
     const int* count;
     double* phi;
 };
-constexpr int PMAT_THREADS = 256;
 constexpr int PMAT_MAXK = 24;        // coefficients held in registers per thread
-inline size_t wls_pmat_smem(int G, int S_pad) { return (size_t)(G - 1) * S_pad * sizeof(float); }
+inline int wls_pmat_kpad(int G) { return (G - 1 + 3) / 4 * 4; }       // coefficient rows padded to a multiple of four
+inline size_t wls_pmat_smem(int G, int S_pad, bool as_double) {
+    return (size_t)wls_pmat_kpad(G) * S_pad * (as_double ? sizeof(double) : sizeof(float));
+}
 
-// Persistent CTAs; P resident in shared memory.  Per coalition row: y, then nA multiply-adds in float64.
-__global__ void __launch_bounds__(PMAT_THREADS) wls_pmat_kernel(WlsPmatParams p) {
-    extern __shared__ float s_P[];                       // [(G-1)][S_pad]
-    __shared__ double s_part[PMAT_THREADS / 32][PMAT_MAXK];
+// Persistent CTAs; P resident in shared memory.  Per coalition row: y, then KPAD multiply-adds in float64.
+// KPAD (compile time) = coefficients rounded up to a multiple of four, the padding rows of P are zero: the inner loop has
+// no bounds checks.  PT = double when the table fits shared memory in float64 (converted once per CTA; the float -> double
+// conversions otherwise compete with the log's reciprocal for the XU pipe), float else.
+template <int KPAD, typename PT, int THREADS>
+__global__ void __launch_bounds__(THREADS) wls_pmat_kernel(WlsPmatParams p) {
+    extern __shared__ __align__(16) unsigned char s_praw[];
+    PT* s_P = reinterpret_cast<PT*>(s_praw);                        // [KPAD][S_pad]
+    __shared__ double s_part[THREADS / 32][KPAD];
     __shared__ LogTabEntry s_logtab[DKS_LOGTAB_SIZE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int G = p.G, nA = G - 1;
     const int cnt = *p.count;
     if ((int)blockIdx.x >= cnt) return;
     if (threadIdx.x < DKS_LOGTAB_SIZE) logtab_fill(s_logtab, threadIdx.x);
-    for (int idx = threadIdx.x; idx < nA * p.S_pad; idx += PMAT_THREADS) s_P[idx] = p.pmat[idx];
+    for (int idx = threadIdx.x; idx < KPAD * p.S_pad; idx += THREADS) s_P[idx] = idx < nA * p.S_pad ? (PT)p.pmat[idx] : (PT)0;
     __syncthreads();
     const double lf1 = p.linkfnull[1], f1 = p.fnull[1], inv_n = 1.0 / (double)p.N;
     const size_t slab = (size_t)p.n * G;
     int i_next = p.list[blockIdx.x];
     double delta_next = p.dlink[(size_t)i_next * p.C + 1];
+    constexpr int INFLIGHT = THREADS >= 512 ? 4 : 8;                  // independent loads in flight per thread
     for (int m = blockIdx.x; m < cnt; m += gridDim.x) {
         const int i = i_next;
         const double delta = delta_next;
@@ -326,42 +522,39 @@ __global__ void __launch_bounds__(PMAT_THREADS) wls_pmat_kernel(WlsPmatParams p)
             delta_next = p.dlink[(size_t)i_next * p.C + 1];
         }
         const float2* sums = p.sums + (size_t)i * p.S_pad;
-        double Tk[PMAT_MAXK];
+        double Tk[KPAD];
 #pragma unroll
-        for (int k = 0; k < PMAT_MAXK; ++k) Tk[k] = 0.0;
-        for (int s0 = 0; s0 < p.S; s0 += 8 * PMAT_THREADS) {
-            float2 a[8];                               // eight independent loads in flight per thread
+        for (int k = 0; k < KPAD; ++k) Tk[k] = 0.0;
+        for (int s0 = 0; s0 < p.S; s0 += INFLIGHT * THREADS) {
+            float2 a[INFLIGHT];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int s = s0 + r * PMAT_THREADS + threadIdx.x;
+            for (int r = 0; r < INFLIGHT; ++r) {
+                const int s = s0 + r * THREADS + threadIdx.x;
                 a[r] = s < p.S ? sums[s] : make_float2(1.f, 1.f);
             }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int s = s0 + r * PMAT_THREADS + threadIdx.x;
+            for (int r = 0; r < INFLIGHT; ++r) {
+                const int s = s0 + r * THREADS + threadIdx.x;
                 if (s < p.S) {
                     double y;
                     if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(a[r].x, a[r].y, s_logtab) - lf1;
                     else y = (p.uniform_w ? (double)a[r].x * inv_n : (double)a[r].x) - f1;
 #pragma unroll
-                    for (int k = 0; k < PMAT_MAXK; ++k)
-                        if (k < nA) Tk[k] = fma((double)s_P[(size_t)k * p.S_pad + s], y, Tk[k]);
+                    for (int k = 0; k < KPAD; ++k) Tk[k] = fma((double)s_P[(size_t)k * p.S_pad + s], y, Tk[k]);
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < PMAT_MAXK; ++k) {
-            if (k < nA) {
-                const double r = warp_sum(Tk[k]);
-                if (lane == 0) s_part[wib][k] = r;
-            }
+        for (int k = 0; k < KPAD; ++k) {
+            const double r = warp_sum(Tk[k]);
+            if (lane == 0) s_part[wib][k] = r;
         }
         __syncthreads();
         if (wib == 0) {
             double beta = 0.0;
             if (lane < nA) {
 #pragma unroll
-                for (int wq = 0; wq < PMAT_THREADS / 32; ++wq) beta += s_part[wq][lane];      // fixed order: reproducible
+                for (int wq = 0; wq < THREADS / 32; ++wq) beta += s_part[wq][lane];      // fixed order: reproducible
                 beta -= delta * p.dvec[lane];
             }
             const double sum = warp_sum(beta);
@@ -374,6 +567,36 @@ __global__ void __launch_bounds__(PMAT_THREADS) wls_pmat_kernel(WlsPmatParams p)
         }
         __syncthreads();
     }
+}
+
+// picks the instantiation; returns false when no variant fits shared memory
+inline bool launch_wls_pmat(const WlsPmatParams& p, int n, int sm_count, int max_smem, cudaStream_t stream, cudaError_t* err) {
+    const int kpad = wls_pmat_kpad(p.G);
+    const size_t sm_d = wls_pmat_smem(p.G, p.S_pad, true), sm_f = wls_pmat_smem(p.G, p.S_pad, false);
+    const bool as_double = sm_d + 8192 <= (size_t)max_smem;
+    if (!as_double && sm_f + 8192 > (size_t)max_smem) return false;
+    const size_t smem = as_double ? sm_d : sm_f;
+    int per_sm = (int)((size_t)max_smem / (smem + 8192));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const int grid = n < sm_count * per_sm ? n : sm_count * per_sm;
+    *err = cudaSuccess;
+#define DKS_PM(K)                                                                                                         \
+    case K:                                                                                                               \
+        if (as_double) {                                                                                                  \
+            *err = cudaFuncSetAttribute(wls_pmat_kernel<K, double, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (*err == cudaSuccess) wls_pmat_kernel<K, double, 512><<<grid, 512, smem, stream>>>(p);                     \
+        } else {                                                                                                          \
+            *err = cudaFuncSetAttribute(wls_pmat_kernel<K, float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (*err == cudaSuccess) wls_pmat_kernel<K, float, 256><<<grid, 256, smem, stream>>>(p);                      \
+        }                                                                                                                 \
+        break;
+    switch (kpad) {
+        DKS_PM(4) DKS_PM(8) DKS_PM(12) DKS_PM(16) DKS_PM(20) DKS_PM(24)
+        default: return false;
+    }
+#undef DKS_PM
+    return true;
 }
 
 // Persistent CTAs of 8 warps, each looping over instances: y = link(ey) - link(fnull) per coalition, E^T W y in 2^-40
