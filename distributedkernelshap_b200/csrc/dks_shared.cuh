@@ -494,8 +494,8 @@ inline size_t wls_pmat_smem(int G, int S_pad, bool as_double) {
 
 // Persistent CTAs; P resident in shared memory.  Per coalition row: y, then KPAD multiply-adds in float64.
 // KPAD (compile time) = coefficients rounded up to a multiple of four, the padding rows of P are zero: the inner loop has
-// no bounds checks.  PT = double when the table fits shared memory in float64 (converted once per CTA; the float -> double
-// conversions otherwise compete with the log's reciprocal for the XU pipe), float else.
+// no bounds checks (the checks were a fifth of the instructions).  PT = float by default; a float64 copy of the table
+// (no float -> double conversions in the loop, but half the CTAs per SM) measured slower.
 template <int KPAD, typename PT, int THREADS>
 __global__ void __launch_bounds__(THREADS) wls_pmat_kernel(WlsPmatParams p) {
     extern __shared__ __align__(16) unsigned char s_praw[];
@@ -573,7 +573,11 @@ __global__ void __launch_bounds__(THREADS) wls_pmat_kernel(WlsPmatParams p) {
 inline bool launch_wls_pmat(const WlsPmatParams& p, int n, int sm_count, int max_smem, cudaStream_t stream, cudaError_t* err) {
     const int kpad = wls_pmat_kpad(p.G);
     const size_t sm_d = wls_pmat_smem(p.G, p.S_pad, true), sm_f = wls_pmat_smem(p.G, p.S_pad, false);
-    const bool as_double = sm_d + 8192 <= (size_t)max_smem;
+    // measured on B200 (Adult shape): float32 table, 2 CTAs of 256 threads per SM: 57 us; float64 table, 1 CTA of 512
+    // threads: 90 us.  DKS_PMAT=double selects the float64 variant for comparisons.
+    static int want_double = -1;
+    if (want_double < 0) { const char* e = getenv("DKS_PMAT"); want_double = (e && e[0] == 'd') ? 1 : 0; }
+    const bool as_double = want_double && sm_d + 8192 <= (size_t)max_smem;
     if (!as_double && sm_f + 8192 > (size_t)max_smem) return false;
     const size_t smem = as_double ? sm_d : sm_f;
     int per_sm = (int)((size_t)max_smem / (smem + 8192));
