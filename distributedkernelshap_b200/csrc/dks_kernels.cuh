@@ -203,6 +203,17 @@ __global__ void predict_kernel(const double* __restrict__ X, const double* __res
     for (int c = 0; c < C; ++c) out[(size_t)i * C + c] = o[c];
 }
 
+// Packed fp32 (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per thread in one 64-bit register pair, one issue slot).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
+
 // ------------------------------------------------------------------------------------------------------
 // Preparation: grouped instance contributions, varying_groups(), f(x), link deltas
 // ------------------------------------------------------------------------------------------------------

@@ -70,16 +70,6 @@ __device__ __forceinline__ void single_acc(float A, float dma, float& a1, float&
     a0 = fmaf(ua, r, a0);
 }
 
-// Packed fp32 (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per thread in one 64-bit register pair, one issue slot).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
-}
-
 // Four sigmoids (two pairs, each sharing one reciprocal) in packed arithmetic: da = (dm0, dm1), db = (dm2, dm3) pair up as
 // (0,2) and (1,3).  10 packed ops + 2 MUFU per four elements (pair_acc: 11 + 1 per two).
 __device__ __forceinline__ void quad_acc(f32x2 A2, f32x2 da, f32x2 db, f32x2 one2, f32x2 two2, f32x2& a1, f32x2& a0) {

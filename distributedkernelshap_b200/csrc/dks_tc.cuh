@@ -289,8 +289,35 @@ __device__ __forceinline__ void consume_pair(float ta, float tb, float wa, float
     }
 }
 
+// Uniform background weights: four columns at a time in packed fp32 (FFMA2/FMUL2/FADD2).  With u = 2^t per column and
+// the columns paired (0,2), (1,3):  p1a + p1b = (2 + sm) / (1 + sm + q),  p0a + p0b = (sm + 2q) / (1 + sm + q),
+// sm = ua + ub, q = ua ub -- one reciprocal per pair, 8 packed ops + 4 clamps + 6 MUFU per four columns.
+__device__ __forceinline__ void consume_quad(float t0, float t1, float t2, float t3, f32x2& a1, f32x2& a0) {
+    const f32x2 u = f2_pack(ex2_approx(fminf(t0, T_CLAMP)), ex2_approx(fminf(t1, T_CLAMP)));
+    const f32x2 v = f2_pack(ex2_approx(fminf(t2, T_CLAMP)), ex2_approx(fminf(t3, T_CLAMP)));
+    const f32x2 one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
+    const f32x2 q = f2_mul(u, v), sm = f2_add(u, v);
+    const f32x2 s1 = f2_add(sm, one2);
+    float dlo, dhi;
+    f2_unpack(f2_add(q, s1), dlo, dhi);
+    const f32x2 r = f2_pack(rcp_approx(dlo), rcp_approx(dhi));
+    a1 = f2_fma(r, f2_add(s1, one2), a1);
+    a0 = f2_fma(r, f2_fma(two2, q, sm), a0);
+}
+
 template <bool UW>
 __device__ __forceinline__ void consume16(const float (&v)[16], const float* __restrict__ wb, float& acc1, float& acc0) {
+    if (UW) {
+        f32x2 p1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, p0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) consume_quad(v[jj], v[jj + 1], v[jj + 2], v[jj + 3], p1[(jj >> 2) & 1], p0[(jj >> 2) & 1]);
+        float x0, x1, y0, y1;
+        f2_unpack(f2_add(p1[0], p1[1]), x0, x1);
+        f2_unpack(f2_add(p0[0], p0[1]), y0, y1);
+        acc1 += x0 + x1;
+        acc0 += y0 + y1;
+        return;
+    }
     float a1[2] = {0.f, 0.f}, a0[2] = {0.f, 0.f};
 #pragma unroll
     for (int jj = 0; jj < 16; jj += 2)
