@@ -312,8 +312,8 @@ def run_ours(args):
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     mufu_peak = 148 * 16 * sm_mhz * 1e6                          # MUFU ops/s at the observed clock (16 lanes/clk/SM, measured)
     kname, mufu_per_elem = {
-        "auto": ("explain_shared_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
-        "shared": ("explain_shared_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
+        "auto": ("explain_shared_tmem_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
+        "shared": ("explain_shared_tmem_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
         "tcgen05": ("explain_tcgen05_kernel", 1.5), "simt": ("explain_simt_kernel", 2.0)}[engine.kernel]
     if args.plan_mode == "per_instance" and engine.kernel != "simt":
         kname, mufu_per_elem = "sample_plans_kernel + explain_tcgen05_kernel (per-instance plans)", 1.5
