@@ -295,19 +295,48 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
         const int ntab = (G + 3) / 4;
         const f32x2 one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
 
-        for (int m = part; m < cnt; m += nparts) {
-            const int i = p.list[m];
-            const double* xt = p.XT + (size_t)i * ntab * 16;
-            double a0 = 0.0, a1 = 0.0;
+        // Up to 16 groups (four nibbles): the table entries of the NEXT instance are loaded one iteration ahead (the row's
+        // nibbles, hence the offsets, do not depend on the instance), so neither the index load nor the table load sits
+        // in front of A.  Wider problems load in place: their per-instance arithmetic is long enough to hide it.
+        const bool ahead = ntab <= 4;
+        int off[4];
 #pragma unroll
-            for (int w = 0; w < W; ++w) {
-#pragma unroll 4
-                for (int t = 0; t < 16 && 16 * w + t < ntab; t += 2) {
-                    a0 += __ldg(xt + (16 * w + t) * 16 + (int)((zz[w] >> (4 * t)) & 15ull));
-                    if (16 * w + t + 1 < ntab) a1 += __ldg(xt + (16 * w + t + 1) * 16 + (int)((zz[w] >> (4 * t + 4)) & 15ull));
+        for (int t = 0; t < 4; ++t) off[t] = t * 16 + (int)((zz[0] >> (4 * t)) & 15ull);
+        int i_cur = part < cnt ? p.list[part] : 0;
+        int i_nx = part + nparts < cnt ? p.list[part + nparts] : 0;
+        double nx[4] = {0.0, 0.0, 0.0, 0.0};
+        if (ahead && part < cnt) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (t < ntab) nx[t] = __ldg(p.XT + (size_t)i_cur * ntab * 16 + off[t]);
+        }
+        for (int m = part; m < cnt; m += nparts) {
+            int i;
+            double a;
+            if (ahead) {
+                i = i_cur;
+                a = (nx[0] + nx[1]) + (nx[2] + nx[3]);
+                i_cur = i_nx;
+                if (m + nparts < cnt) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t < ntab) nx[t] = __ldg(p.XT + (size_t)i_cur * ntab * 16 + off[t]);
                 }
+                if (m + 2 * nparts < cnt) i_nx = p.list[m + 2 * nparts];
+            } else {
+                i = p.list[m];
+                const double* xt = p.XT + (size_t)i * ntab * 16;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+#pragma unroll 4
+                    for (int t = 0; t < 16 && 16 * w + t < ntab; t += 2) {
+                        a0 += __ldg(xt + (16 * w + t) * 16 + (int)((zz[w] >> (4 * t)) & 15ull));
+                        if (16 * w + t + 1 < ntab) a1 += __ldg(xt + (16 * w + t + 1) * 16 + (int)((zz[w] >> (4 * t + 4)) & 15ull));
+                    }
+                }
+                a = a0 + a1;
             }
-            double a = a0 + a1;
             a = fmin(fmax(a, -120.0), 120.0);
             const double an = rint(a);
             const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
