@@ -239,7 +239,7 @@ class GpuKernelExplainer:
             self._last_rows = n
             return merged if self.vector_out else merged[0]
 
-        phi = np.zeros((self.D, n, G))
+        phi = np.empty((self.D, n, G))      # the device writes every entry (zeros for groups that do not vary)
         self._link_fx_parts = []
         if self.plan_mode == "per_instance":
             # the device draws each row's plan from (seed, global row index): tell it where this block starts
