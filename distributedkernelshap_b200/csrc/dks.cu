@@ -377,7 +377,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums);
-    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
@@ -813,9 +813,18 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
         dz = ctx->d_extz; dw = ctx->d_extw;
     }
     TRY(launch_explain(ctx, ctx->d_phi, dz, dw, ext_stride));
-    CUDA_TRY(cudaMemcpyAsync(phi_host, ctx->d_phi, sizeof(double) * need_phi, cudaMemcpyDeviceToHost, ctx->stream));
+    // results travel through a pinned staging buffer: one asynchronous DMA + one host memcpy instead of the driver's
+    // chunked pageable path (the caller's array is ordinary NumPy memory)
+    if (need_phi > ctx->cap_phi_pin) {
+        if (ctx->h_phi_pin) cudaFreeHost(ctx->h_phi_pin);
+        ctx->h_phi_pin = nullptr; ctx->cap_phi_pin = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&ctx->h_phi_pin, sizeof(double) * need_phi, cudaHostAllocDefault));
+        ctx->cap_phi_pin = need_phi;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_phi_pin, ctx->d_phi, sizeof(double) * need_phi, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(phi_host, ctx->h_phi_pin, sizeof(double) * need_phi);
     return check_status(ctx);
 }
 

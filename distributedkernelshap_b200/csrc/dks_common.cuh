@@ -154,6 +154,8 @@ struct dks_ctx {
     size_t cap_sums = 0;
     double* d_phi = nullptr;
     size_t cap_phi = 0;
+    double* h_phi_pin = nullptr;  // pinned staging for results going to pageable host memory
+    size_t cap_phi_pin = 0;
     uint64_t* d_extz = nullptr;
     double* d_extw = nullptr;
     size_t cap_ext = 0;
