@@ -216,7 +216,8 @@ def run_ours(args):
     sv0 = engine.get_explanation(X, nsamples=NSAMPLES, l1_reg=False, silent=True)
 
     # ---------------- device-resident steps: `value` ----------------
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # not the legacy default stream: the engine replays its launch sequence
+    torch.cuda.set_stream(stream)                # as one CUDA graph only on a capturable stream
     engine.set_stream(stream.cuda_stream)
     X_dev = torch.from_numpy(X).cuda()
     phi_dev = torch.empty((C, n, G), dtype=torch.float64, device="cuda")

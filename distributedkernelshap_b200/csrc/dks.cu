@@ -80,7 +80,14 @@ int ensure_workspace(dks_ctx* ctx, int n) {
     TRY(dev_alloc(&ctx->d_idx_full, (size_t)n));
     TRY(dev_alloc(&ctx->d_idx_other, (size_t)n));
     ctx->cap_n = n;
+    ctx->epoch++;            // buffers moved: a captured graph holds the old addresses
     return DKS_OK;
+}
+
+// timing events: inside a stream capture they become external event-record nodes, so dks_last_timings keeps working
+// for graph launches
+cudaError_t record_ev(dks_ctx* ctx, int k) {
+    return cudaEventRecordWithFlags(ctx->ev[k], ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
 int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
@@ -88,7 +95,7 @@ int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
     TRY(ensure_workspace(ctx, n));
     // histogram, status word and list counters are adjacent: one memset
     CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4), ctx->stream));
-    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CUDA_TRY(record_ev(ctx, 0));
     int ipb = 256 / G;
     if (ipb < 1) ipb = 1;
     size_t psm = sizeof(double) * (size_t)ipb * G * ctx->R + (size_t)ipb * G;
@@ -99,7 +106,7 @@ int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
         (ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->R == 1) ? ctx->d_XT : nullptr, ctx->scale);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CUDA_TRY(record_ev(ctx, 1));
     ctx->cur_n = n;
     ctx->cur_X = X_dev;
     ctx->prepared = true;
@@ -124,19 +131,16 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         const size_t need = (size_t)n * stride;
         if (need > ctx->cap_gen) {
             TRY(dev_alloc(&ctx->d_genz, need)); TRY(dev_alloc(&ctx->d_genw, need));
-            ctx->cap_gen = need;
+            ctx->cap_gen = need; ctx->epoch++;
         }
         const int nAmax = ctx->G > 1 ? ctx->G - 1 : 1;
         const int fstride = nAmax * nAmax;
         const size_t needf = (size_t)n * fstride;
         if (needf > ctx->cap_genf) {
             TRY(dev_alloc(&ctx->d_genchol, needf)); TRY(dev_alloc(&ctx->d_genainv, needf));
-            ctx->cap_genf = needf;
+            ctx->cap_genf = needf; ctx->epoch++;
         }
-        if (!ctx->d_sinfo) TRY(dev_alloc(&ctx->d_sinfo, (size_t)(DKS_MAX_GROUPS + 1)));
-        if (!ctx->d_afix) TRY(dev_alloc(&ctx->d_afix, (size_t)(DKS_MAX_GROUPS + 1)));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_sinfo, ctx->h_sinfo, sizeof(ctx->h_sinfo), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_afix, ctx->h_afix, sizeof(ctx->h_afix), cudaMemcpyHostToDevice, ctx->stream));
+        REQUIRE(ctx->d_sinfo && ctx->d_afix, "per-instance plans: dks_set_plan_sampling has not been called");
         // table sized for the largest sampled part among the plans set (a plan's sampled rows <= its S)
         int max_left = 32;
         for (int M = 2; M <= ctx->G && M <= DKS_MAX_GROUPS; ++M)
@@ -214,7 +218,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     }
 
     int kernel = ctx->kernel_choice;
-    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(record_ev(ctx, 2));
 
     // ---- shared-plan fast path: instances whose varying set is all G groups, evaluated against the plan's Dm table
     const int G = ctx->G;
@@ -227,7 +231,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     if (fast) {
         const int S = pg.S, S_pad = pg.S_pad;
         size_t need = (size_t)n * S_pad;
-        if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; }
+        if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; ctx->epoch++; }
         dks::shared_path::SharedParams sp;
         sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
         sp.DmT = pg.dmT; sp.z = pg.z; sp.XT = ctx->d_XT; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
@@ -278,7 +282,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         dks::flag_unsupported_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_counts + 1, G, ctx->d_status);
         ctx->launches += 1;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CUDA_TRY(record_ev(ctx, 3));
         return DKS_OK;
     }
     if (kernel == DKS_KERNEL_AUTO || kernel == DKS_KERNEL_SHARED)
@@ -304,7 +308,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         ctx->launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(record_ev(ctx, 3));
     return DKS_OK;
 }
 
@@ -350,6 +354,7 @@ int dks_create(dks_ctx** out, int device) {
                     prop.major, prop.minor);
     dks_ctx* ctx = new dks_ctx();
     ctx->device = device;
+    { const char* e = getenv("DKS_GRAPH"); ctx->graph_enabled = !(e && e[0] == '0'); }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
@@ -370,6 +375,7 @@ int dks_destroy(dks_ctx* ctx) {
     if (!ctx) return DKS_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
     dev_free(&ctx->d_bg); dev_free(&ctx->d_wbg); dev_free(&ctx->d_W); dev_free(&ctx->d_b);
     dev_free(&ctx->d_goff); dev_free(&ctx->d_gcols); dev_free(&ctx->d_colmin); dev_free(&ctx->d_colmax);
     dev_free(&ctx->d_colnan); dev_free(&ctx->d_BW); dev_free(&ctx->d_scores); dev_free(&ctx->d_Bbar);
@@ -545,6 +551,7 @@ int dks_fit(dks_ctx* ctx) {
     }
     TRY(dks::tc_fit(ctx));
     ctx->fitted = true;
+    ctx->epoch++;
     return DKS_OK;
 }
 
@@ -663,6 +670,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         }
     }
     ctx->h_plans[M] = pd;
+    ctx->epoch++;
     ctx->h_afix[M] = nullptr;                       // sampling info of a replaced plan is stale
     memset(&ctx->h_sinfo[M], 0, sizeof(ctx->h_sinfo[M]));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
@@ -677,6 +685,7 @@ int dks_clear_plans(dks_ctx* ctx) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (void* p : ctx->plan_allocs) cudaFree(p);
     ctx->plan_allocs.clear();
+    ctx->epoch++;
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
     memset(ctx->h_afix, 0, sizeof(ctx->h_afix));
     memset(ctx->h_sinfo, 0, sizeof(ctx->h_sinfo));
@@ -711,6 +720,13 @@ int dks_set_plan_sampling(dks_ctx* ctx, int M, int nfixed, int n_full, int n_pai
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     ctx->h_afix[M] = af;
+    // device copies of the tables the sampler reads (kept current here, not per explain call)
+    if (!ctx->d_sinfo) TRY(dev_alloc(&ctx->d_sinfo, (size_t)(DKS_MAX_GROUPS + 1)));
+    if (!ctx->d_afix) TRY(dev_alloc(&ctx->d_afix, (size_t)(DKS_MAX_GROUPS + 1)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_sinfo, ctx->h_sinfo, sizeof(ctx->h_sinfo), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_afix, ctx->h_afix, sizeof(ctx->h_afix), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->epoch++;
     return DKS_OK;
 }
 
@@ -791,7 +807,75 @@ int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev
     BIND(ctx);
     REQUIRE(phi_dev, "dks_explain_dev: phi is NULL");
     TRY(launch_explain(ctx, phi_dev, ext_zbits_dev, ext_w_dev, ext_stride));
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    return DKS_OK;
+}
+
+static void drop_graph(dks_ctx* ctx) {
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+}
+
+int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
+    BIND(ctx);
+    REQUIRE(ctx->fitted, "dks_run_dev: call dks_fit first");
+    REQUIRE(X_dev && phi_dev && n > 0, "dks_run_dev: bad arguments");
+    dks_ctx::GraphKey key{X_dev, phi_dev, n, ctx->nsamples_req, ctx->kernel_choice, ctx->plan_mode, ctx->row_offset,
+                          (unsigned long long)ctx->sampler_seed, ctx->epoch, ctx->stream};
+    if (ctx->graph_enabled && ctx->gexec && key == ctx->graph_key && ctx->dbg_i < 0) {
+        CUDA_TRY(cudaGraphLaunch(ctx->gexec, ctx->stream));
+        ctx->graph_launches++;
+        ctx->launches += ctx->graph_kernels;
+        return DKS_OK;                          // the status word stays on the device until dks_last_status asks for it
+    }
+    // the second identical call is captured (the first one sized every workspace, so nothing allocates during capture)
+    // (the legacy default stream cannot be captured: callers that want graph replay pass their own stream)
+    const bool capturable = ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread;
+    bool capture = ctx->graph_enabled && capturable && ctx->have_last_key && key == ctx->last_key && ctx->dbg_i < 0;
+    ctx->last_key = key; ctx->have_last_key = true;
+    if (capture) {
+        drop_graph(ctx);
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->graph_enabled = false;          // this stream cannot be captured: plain launches from now on
+            capture = false;
+        } else {
+            ctx->capturing = true;
+        }
+    }
+    const int64_t launches_before = ctx->launches;
+    int rc = launch_prepare(ctx, X_dev, n);
+    if (rc == DKS_OK) rc = launch_explain(ctx, phi_dev, nullptr, nullptr, 0);
+    if (capture) {
+        ctx->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc == DKS_OK && ce == cudaSuccess && graph) {
+            ce = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+            if (ce == cudaSuccess) {
+                ctx->graph_key = key;
+                ctx->graph_kernels = ctx->launches - launches_before;
+                ce = cudaGraphLaunch(ctx->gexec, ctx->stream);      // capturing did not execute anything
+                ctx->graph_launches++;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != DKS_OK) return rc;
+        if (ce != cudaSuccess) {
+            drop_graph(ctx);
+            cudaGetLastError();
+            ctx->graph_enabled = false;                              // fall back to plain launches for good
+            ctx->launches = launches_before;
+            TRY(launch_prepare(ctx, X_dev, n));
+            TRY(launch_explain(ctx, phi_dev, nullptr, nullptr, 0));
+        }
+    } else if (rc != DKS_OK) {
+        return rc;
+    }
+    return DKS_OK;
+}
+
+int dks_graph_launches(dks_ctx* ctx, int64_t* count) {
+    REQUIRE(ctx && count, "dks_graph_launches: bad arguments");
+    *count = ctx->graph_launches;
     return DKS_OK;
 }
 
@@ -830,6 +914,7 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
 
 int dks_last_status(dks_ctx* ctx, int* detail) {
     BIND(ctx);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (detail) *detail = ctx->h_status[1];
     return check_status(ctx);

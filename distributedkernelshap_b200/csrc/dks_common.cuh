@@ -161,6 +161,25 @@ struct dks_ctx {
     size_t cap_ext = 0;
     int h_status[2] = {0, 0};
 
+    // CUDA graph of the device-resident explain sequence (dks_run_dev): captured on the second identical call
+    struct GraphKey {
+        const void* X; void* phi; int n, nsamples, kernel, plan_mode; long long row_offset; unsigned long long seed;
+        unsigned epoch; cudaStream_t stream;
+        bool operator==(const GraphKey& o) const {
+            return X == o.X && phi == o.phi && n == o.n && nsamples == o.nsamples && kernel == o.kernel &&
+                   plan_mode == o.plan_mode && row_offset == o.row_offset && seed == o.seed && epoch == o.epoch &&
+                   stream == o.stream;
+        }
+    };
+    bool graph_enabled = true;    // DKS_GRAPH=0 disables
+    bool capturing = false;
+    bool have_last_key = false;
+    GraphKey last_key{}, graph_key{};
+    cudaGraphExec_t gexec = nullptr;
+    unsigned epoch = 0;           // bumped by everything that changes what the sequence launches (fit, plans, ...)
+    int64_t graph_launches = 0;
+    int64_t graph_kernels = 0;    // kernels one replay of the captured graph launches
+
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
 };

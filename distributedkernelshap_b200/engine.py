@@ -322,8 +322,13 @@ class GpuKernelExplainer:
         buffer ``phi_dev_ptr`` (float64 [C, n, G]) using the shared plans already on the device.  Call ``check_status()``
         after synchronising to learn about missing plans / numerical failures."""
         self._set_nsamples(nsamples)
-        _cabi.check(self.lib.dks_prepare_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n)))
-        _cabi.check(self.lib.dks_explain_dev(self._ctx, C.c_void_p(int(phi_dev_ptr)), None, None, 0))
+        _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n), C.c_void_p(int(phi_dev_ptr))))
+
+    def graph_launches(self):
+        """How many ``explain_device`` calls were replayed as one CUDA-graph launch."""
+        cnt = C.c_int64(0)
+        _cabi.check(self.lib.dks_graph_launches(self._ctx, C.byref(cnt)))
+        return cnt.value
 
     def check_status(self):
         """Synchronise the engine's stream and raise if the last explain reported a problem."""

@@ -132,11 +132,18 @@ int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host);
  * instance i), device pointers for _dev and host pointers for _host. */
 int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev, const double* ext_w_dev,
                     int ext_stride);
+/* prepare + explain for rows resident in device memory with the engine's own plans, as ONE CUDA-graph launch once the
+ * same call (same buffers, n, nsamples, kernel, plans) has been seen twice: the second call captures the sequence (memset,
+ * stage 1, coalition kernels, solve), later ones replay it.  DKS_GRAPH=0 in the environment keeps plain launches.
+ * Asynchronous like dks_explain_dev; dks_last_timings keeps working (external event-record nodes). */
+int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev);
+int dks_graph_launches(dks_ctx* ctx, int64_t* count);
 /* convenience: prepare + explain from/to host memory; H2D, kernels, D2H; synchronises.  This is the call a
  * non-torch host (ctypes / cgo) makes and the one bench.py's end-to-end number goes through. */
 int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
                      const double* ext_w_host, int ext_stride);
-/* status of the last explain (checked after synchronisation): 0 ok, DKS_ERR_PLAN_MISSING, DKS_ERR_NUMERIC;
+/* status of the LAST explain call on this context (the asynchronous calls leave it on the device; this fetches it and
+ * synchronises): 0 ok, DKS_ERR_PLAN_MISSING, DKS_ERR_NUMERIC, DKS_ERR_UNSUPPORTED;
  * *detail = the offending M / instance index. */
 int dks_last_status(dks_ctx* ctx, int* detail);
 
