@@ -483,3 +483,34 @@ def test_two_word_coalition_rows_up_to_128_groups():
         eng.shap_values(X, nsamples=300, l1_reg=False)
     with pytest.raises(NotImplementedError):
         eng.shap_values(X[1:], nsamples=300, l1_reg=False, plans=[None])
+
+
+def test_device_resident_calls_replay_as_one_cuda_graph():
+    """explain_device on a user stream: the second identical call captures the launch sequence, later ones replay it.
+    The graph reads the buffers at launch time, so new data under the same pointers gives new results."""
+    import torch
+    prob = make_problem(seed=51, n=40, N=14, widths=(1, 2, 1, 1, 3, 1, 1, 2))
+    eng = _engine(prob)
+    want = eng.shap_values(prob["X"], nsamples=120, l1_reg=False)           # host path; plans get built here
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng.set_stream(stream.cuda_stream)
+        X_dev = torch.from_numpy(prob["X"]).cuda()
+        phi = torch.zeros((2, 40, 8), dtype=torch.float64, device="cuda")
+        for _ in range(4):
+            eng.explain_device(X_dev.data_ptr(), 40, phi.data_ptr(), nsamples=120)
+        eng.check_status()
+        assert eng.graph_launches() >= 2
+        np.testing.assert_allclose(phi[1].cpu().numpy(), want[1], rtol=0, atol=1e-12)
+        X2 = prob["X"][::-1].copy()
+        X_dev.copy_(torch.from_numpy(X2))
+        eng.explain_device(X_dev.data_ptr(), 40, phi.data_ptr(), nsamples=120)
+        eng.check_status()
+        np.testing.assert_allclose(phi[1].cpu().numpy(), want[1][::-1], rtol=0, atol=1e-12)
+        before = eng.graph_launches()
+        eng.explain_device(X_dev.data_ptr(), 17, phi.data_ptr(), nsamples=120)   # another shape: plain launches
+        eng.check_status()
+        assert eng.graph_launches() == before
+        np.testing.assert_allclose(phi.cpu().numpy().reshape(-1)[17 * 8 * 0:17 * 8].reshape(17, 8), -want[1][::-1][:17],
+                                   rtol=0, atol=1e-12)
+    eng.set_stream(0)
