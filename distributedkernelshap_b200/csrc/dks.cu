@@ -234,7 +234,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; ctx->epoch++; }
         dks::shared_path::SharedParams sp;
         sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
-        sp.DmT = pg.dmT; sp.z = pg.z; sp.XT = ctx->d_XT; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
+        sp.DmT = pg.dmT; sp.dme = pg.dme; sp.z = pg.z; sp.XT = ctx->d_XT; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
         ctx->launches += dks::shared_path::launch_explain_shared(sp, pg.W, ctx->sm_count, ctx->stream) - 1;
         dks::shared_path::WlsSharedParams wp;
         wp.n = n; wp.N = ctx->N; wp.G = G; wp.C = ctx->C; wp.S = S; wp.S_pad = S_pad; wp.link = ctx->link;
@@ -646,13 +646,18 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     if (M == ctx->G && ctx->fitted && ctx->act == DKS_ACT_BINARY_LOGISTIC) {
         // shared-plan fast path: Dm table for the full varying set
         float* dm = nullptr;
+        double* dme = nullptr;
         CUDA_TRY(cudaMalloc((void**)&dm, sizeof(float) * (size_t)ctx->N * pd.S_pad));
-        ctx->plan_allocs.push_back(dm);
+        CUDA_TRY(cudaMalloc((void**)&dme, sizeof(double) * (size_t)pd.S_pad));
+        ctx->plan_allocs.push_back(dm); ctx->plan_allocs.push_back(dme);
         long long total = (long long)ctx->N * pd.S_pad;
+        dks::shared_path::plan_dme_kernel<<<cdiv(pd.S_pad, 128), 128, 0, ctx->stream>>>(dz, W, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
+                                                                                       ctx->N, ctx->G, ctx->scale, dme);
         dks::shared_path::plan_dm_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(dz, W, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
-                                                                                      ctx->N, ctx->G, ctx->scale, dm);
-        ctx->launches += 1;
+                                                                                      ctx->N, ctx->G, ctx->scale, dme, dm);
+        ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
+        pd.dme = dme;
         pd.dmT = dm;
         // projection form of the solve: P = inv(E^T W E) E^T W and d = P z_L
         if (W == 1 && M - 1 <= dks::shared_path::PMAT_MAXK &&

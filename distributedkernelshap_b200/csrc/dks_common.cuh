@@ -17,7 +17,8 @@ struct PlanDev {
     const double* w;     // [S] kernel weights
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
     const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
-    const float* dmT;    // [N][S_pad] 2^(scaled background part of the score) for the full varying set (shared fast path)
+    const float* dmT;    // [N][S_pad] 2^(scaled background part of the score - dme[s]) for the full varying set (shared fast path)
+    const double* dme;   // [S_pad] row exponents: Dm rows are normalised so that their largest entry is ~1
     const float* pmat;   // [(M-1)][S_pad] P = inv(E^T W E) E^T W (float32): beta = P y - delta * dvec
     const double* dvec;  // [(M-1)] P z_L
     int S;

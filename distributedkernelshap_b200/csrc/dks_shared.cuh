@@ -20,28 +20,45 @@ constexpr int MAXN = 128;            // background rows held in registers per la
 constexpr int WARPS_PER_CTA = 12;
 constexpr float U_CLAMP = 1.152921504606846976e18f;   // 2^60: (1 + ua)(1 + ub) stays finite in fp32
 
-// DmT[j][s] = 2^(scale * (score_j - sum_k z_sk BW[j][k]))  for the full varying set (k = group index), float32,
-// transposed so that consecutive coalitions are contiguous (coalesced row loads by lanes)
+// d(s, j) = scale * (score_j - sum_k z_sk BW[j][k])  for the full varying set (k = group index), in log2 units.
+// Rows are normalised: dme[s] = rint(max_j d(s, j)), DmT[j][s] = 2^(d(s, j) - dme[s]) <= sqrt(2), float32, transposed so that
+// consecutive coalitions are contiguous (coalesced row loads by lanes).  The exponent goes back in through a(i, s), so
+// products of two entries of a row (the kernel stores pair sums and pair products) cannot overflow or vanish together.
+__device__ __forceinline__ double plan_d(const uint64_t* __restrict__ zz, const double* __restrict__ BW,
+                                         const double* __restrict__ scores, int j, int G, double scale) {
+    double c = 0.0;
+    for (int k = 0; k < G; ++k)
+        if ((zz[k >> 6] >> (k & 63)) & 1ull) c += BW[(size_t)j * G + k];
+    return scale * (scores[j] - c);
+}
+__global__ void plan_dme_kernel(const uint64_t* __restrict__ z, int W, int S, int S_pad, const double* __restrict__ BW,
+                                const double* __restrict__ scores, int N, int G, double scale, double* __restrict__ dme) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S_pad) return;
+    double mx = 0.0;
+    if (s < S) {
+        mx = -1.0e300;
+        for (int j = 0; j < N; ++j) mx = fmax(mx, plan_d(z + (size_t)s * W, BW, scores, j, G, scale));
+        mx = rint(mx);
+    }
+    dme[s] = mx;
+}
 __global__ void plan_dm_kernel(const uint64_t* __restrict__ z, int W, int S, int S_pad, const double* __restrict__ BW,
-                               const double* __restrict__ scores, int N, int G, double scale, float* __restrict__ DmT) {
+                               const double* __restrict__ scores, int N, int G, double scale, const double* __restrict__ dme,
+                               float* __restrict__ DmT) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * S_pad) return;
     const int j = idx / S_pad, s = idx - j * S_pad;
     float out = 0.f;
-    if (s < S) {
-        const uint64_t* zz = z + (size_t)s * W;
-        double c = 0.0;
-        for (int k = 0; k < G; ++k)
-            if ((zz[k >> 6] >> (k & 63)) & 1ull) c += BW[(size_t)j * G + k];
-        out = (float)exp2(scale * (scores[j] - c));
-    }
+    if (s < S) out = (float)exp2(plan_d(z + (size_t)s * W, BW, scores, j, G, scale) - dme[s]);
     DmT[idx] = out;
 }
 
 struct SharedParams {
     int n, N, G, S, S_pad;
     double scale;
-    const float* DmT;        // [N][S_pad]
+    const float* DmT;        // [N][S_pad] rows normalised by 2^-dme[s]
+    const double* dme;       // [S_pad]
     const uint64_t* z;       // [S][W]
     const double* XT;        // [n][ceil(G/4)][16] nibble tables: scale * sum of the contributions a nibble selects
     const int* list;         // instances on this path
@@ -168,6 +185,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
 #pragma unroll
     for (int w = 0; w < W; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
     const int nfull = N / 16;
+    const double es = p.dme[s];                          // exponent the row of Dm was normalised by
 
     const int ntab = (G + 3) / 4;
     for (int m = part; m < cnt; m += nparts) {
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(S
                 if (16 * w + t + 1 < ntab) a1 += __ldg(xt + (16 * w + t + 1) * 16 + (int)((zz[w] >> (4 * t + 4)) & 15ull));
             }
         }
-        double a = a0 + a1;
+        double a = (a0 + a1) + es;
         a = fmin(fmax(a, -120.0), 120.0);
         const double an = rint(a);
         const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
@@ -228,23 +246,35 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, float v0, float v1, flo
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// The same four sigmoids from what tensor memory holds for a quad of columns (0,2) (1,3): ds = (dm0 + dm2, dm1 + dm3) and
+// dq = (dm0 dm2, dm1 dm3), both independent of the instance:  sm = A ds,  q = A^2 dq.  7 packed ops + 2 MUFU per four
+// elements (A2 = (A, A), AA2 = (A^2, A^2), AA2x2 = 2 AA2).
+__device__ __forceinline__ void quad_acc_sq(f32x2 A2, f32x2 AA2, f32x2 AA2x2, f32x2 ds, f32x2 dq, f32x2 one2, f32x2 two2,
+                                            f32x2& a1, f32x2& a0) {
+    const f32x2 sm = f2_mul(A2, ds);
+    const f32x2 t1 = f2_add(sm, one2);
+    const f32x2 den = f2_fma(AA2, dq, t1);
+    const f32x2 w = f2_fma(AA2x2, dq, sm);
+    float dlo, dhi;
+    f2_unpack(den, dlo, dhi);
+    const f32x2 r = f2_pack(rcp_approx(dlo), rcp_approx(dhi));
+    a1 = f2_fma(r, f2_add(sm, two2), a1);
+    a0 = f2_fma(r, w, a0);
+}
+
 // one 16-column chunk of a row: four packed quads (or the clamped scalar pairs), NV = valid columns of this chunk
-template <bool CLAMP, int NV>
-__device__ __forceinline__ void chunk_sums(const float (&v)[16], float A, f32x2 A2, f32x2 one2, f32x2 two2, f32x2 (&acc1)[2],
-                                           f32x2 (&acc0)[2], float& t1s, float& t0s) {
-    if (!CLAMP) {
+// v holds, per full quad of columns, (ds.lo, ds.hi, dq.lo, dq.hi); columns past the last full quad of the tail chunk are
+// raw Dm values.
+template <int NV>
+__device__ __forceinline__ void chunk_sums(const float (&v)[16], float A, f32x2 A2, f32x2 AA2, f32x2 AA2x2, f32x2 one2,
+                                           f32x2 two2, f32x2 (&acc1)[2], f32x2 (&acc0)[2], float& t1s, float& t0s) {
 #pragma unroll
-        for (int jj = 0; jj + 3 < NV; jj += 4)
-            quad_acc(A2, f2_pack(v[jj], v[jj + 1]), f2_pack(v[jj + 2], v[jj + 3]), one2, two2, acc1[(jj >> 2) & 1],
-                     acc0[(jj >> 2) & 1]);
-        constexpr int Q = NV & ~3;
-        if ((NV & 3) >= 2) pair_acc<false>(A, v[Q], v[Q + 1], t1s, t0s);
-        if (NV & 1) single_acc(A, v[NV - 1], t1s, t0s);
-    } else {
-#pragma unroll
-        for (int jj = 0; jj + 1 < NV; jj += 2) pair_acc<true>(A, v[jj], v[jj + 1], t1s, t0s);
-        if (NV & 1) single_acc(A, v[NV - 1], t1s, t0s);
-    }
+    for (int jj = 0; jj + 3 < NV; jj += 4)
+        quad_acc_sq(A2, AA2, AA2x2, f2_pack(v[jj], v[jj + 1]), f2_pack(v[jj + 2], v[jj + 3]), one2, two2, acc1[(jj >> 2) & 1],
+                    acc0[(jj >> 2) & 1]);
+    constexpr int Q = NV & ~3;
+    if ((NV & 3) >= 2) pair_acc<false>(A, v[Q], v[Q + 1], t1s, t0s);
+    if (NV & 1) single_acc(A, v[NV - 1], t1s, t0s);
 }
 
 template <int NTAIL, int W>
@@ -270,14 +300,22 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
         const int nfull = N / 16;
         // this warp's slice of tensor memory: its lane quarter, column range warp / 4
         const uint32_t taddr = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * cstride);
-        float dmax = 0.f;
+        const double es = p.dme[s];                      // exponent the row of Dm was normalised by (entries <= sqrt 2)
         for (int c = 0; c * 16 < N; ++c) {
             float v[16];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const int j = c * 16 + jj;
                 v[jj] = j < N ? p.DmT[(size_t)j * p.S_pad + s] : 0.f;
-                dmax = fmaxf(dmax, v[jj]);
+            }
+            // every full quad of columns (0,2) (1,3) is stored as pair sums and pair products
+            const int nv = c < nfull ? 16 : NTAIL;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+                if (jj + 3 < nv) {
+                    const float d0 = v[jj], d1 = v[jj + 1], d2 = v[jj + 2], d3 = v[jj + 3];
+                    v[jj] = d0 + d2; v[jj + 1] = d1 + d3; v[jj + 2] = d0 * d2; v[jj + 3] = d1 * d3;
+                }
             }
             if (c < nfull) {
                 tmem_st16(taddr + c * 16, v);
@@ -337,11 +375,28 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
                 }
                 a = a0 + a1;
             }
+            a += es;
             a = fmin(fmax(a, -120.0), 120.0);
             const double an = rint(a);
             const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
-            const bool risky = __any_sync(0xffffffffu, A * dmax > 1.0e18f);
+            // A^2 must stay finite in fp32 (the normalised entries are <= sqrt 2, so A bounds every u): rows beyond that
+            // take the clamped scalar path on the raw row from global memory (rare: saturated scores)
+            const bool risky = __any_sync(0xffffffffu, A > 1.0e18f);
+            if (risky) {
+                float r1 = 0.f, r0 = 0.f;
+                for (int j = 0; j + 1 < N; j += 2)
+                    pair_acc<true>(A, p.DmT[(size_t)j * p.S_pad + s], p.DmT[(size_t)(j + 1) * p.S_pad + s], r1, r0);
+                if (N & 1) single_acc(A, p.DmT[(size_t)(N - 1) * p.S_pad + s], r1, r0);
+                if (s < p.S) {
+                    float2* dst = p.sums + (size_t)i * p.S_pad + s;
+                    if (p.accumulate) { const float2 o = *dst; r1 += o.x; r0 += o.y; }
+                    *dst = make_float2(r1, r0);
+                }
+                continue;
+            }
             const f32x2 A2 = f2_pack(A, A);
+            const float AA = A * A;
+            const f32x2 AA2 = f2_pack(AA, AA), AA2x2 = f2_pack(2.f * AA, 2.f * AA);
             f32x2 acc1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, acc0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
             float t1s = 0.f, t0s = 0.f;
             // chunks of 16 columns, the next one in flight while this one is consumed
@@ -351,23 +406,13 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
             for (int c = 0; c < nch; c += 2) {
                 tc::tmem_ld_wait(va);
                 if (c + 1 < nch) tc::tmem_ld16(taddr + (c + 1) * 16, vb);
-                if (c < nfull) {
-                    if (risky) chunk_sums<true, 16>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                    else chunk_sums<false, 16>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                } else if (NTAIL > 0) {
-                    if (risky) chunk_sums<true, NTAIL>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                    else chunk_sums<false, NTAIL>(va, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                }
+                if (c < nfull) chunk_sums<16>(va, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
+                else if (NTAIL > 0) chunk_sums<NTAIL>(va, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
                 if (c + 1 < nch) {
                     tc::tmem_ld_wait(vb);
                     if (c + 2 < nch) tc::tmem_ld16(taddr + (c + 2) * 16, va);
-                    if (c + 1 < nfull) {
-                        if (risky) chunk_sums<true, 16>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                        else chunk_sums<false, 16>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                    } else if (NTAIL > 0) {
-                        if (risky) chunk_sums<true, NTAIL>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                        else chunk_sums<false, NTAIL>(vb, A, A2, one2, two2, acc1, acc0, t1s, t0s);
-                    }
+                    if (c + 1 < nfull) chunk_sums<16>(vb, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
+                    else if (NTAIL > 0) chunk_sums<NTAIL>(vb, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
                 }
             }
             float q0, q1, q2, q3;
