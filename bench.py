@@ -326,10 +326,10 @@ def run_ours(args):
                 "mufu_ops_per_elem": mufu_per_elem, "mufu_ops_per_s": mufu_per_elem * elems / (k_ms * 1e-3),
                 "mufu_frac": mufu_per_elem * elems / (k_ms * 1e-3) / mufu_peak}
     if engine.kernel in ("auto", "shared") and args.plan_mode == "shared":
-        # shared-plan path: 10 packed fp32 ops (FFMA2/FMUL2/FADD2, two lanes each, half issue rate: measured,
-        # profiles/r1_ffma2_probe_b200.txt) per four sigmoids = 5 fp32 lane-ops per element against 128 lanes/clk/SM
+        # shared-plan path: 7 packed fp32 ops (FFMA2/FMUL2/FADD2, two lanes each, half issue rate: measured,
+        # profiles/r1_ffma2_probe_b200.txt) per four sigmoids = 3.5 fp32 lane-ops per element against 128 lanes/clk/SM
         fp32_peak = 148 * 128 * sm_mhz * 1e6
-        roofline.update({"fp32_lane_ops_per_elem": 5.0, "fp32_pipe_frac": 5.0 * elems / (k_ms * 1e-3) / fp32_peak})
+        roofline.update({"fp32_lane_ops_per_elem": 3.5, "fp32_pipe_frac": 3.5 * elems / (k_ms * 1e-3) / fp32_peak})
 
     line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -514,3 +514,24 @@ def test_device_resident_calls_replay_as_one_cuda_graph():
         np.testing.assert_allclose(phi.cpu().numpy().reshape(-1)[17 * 8 * 0:17 * 8].reshape(17, 8), -want[1][::-1][:17],
                                    rtol=0, atol=1e-12)
     eng.set_stream(0)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "tcgen05", "simt"])
+def test_small_probabilities_keep_their_relative_precision(kernel):
+    """Scores around -10 (p1 ~ 1e-9, about as far as the reference's own float64 ``log(x / (1 - x))`` stays meaningful for
+    the complementary class): 2^t reaches 2^30 and the shared-plan kernel works with A and A^2 of the normalised rows.
+    p1 and p0 are accumulated separately, so the small class keeps its relative precision."""
+    from distributedkernelshap_b200.predictors import LinearSoftmaxClassifier
+    prob = make_problem(seed=61, n=12, N=20, widths=(1, 1, 2, 1, 1, 3, 1, 1))
+    rng = np.random.default_rng(5)
+    prob["clf"] = LinearSoftmaxClassifier(rng.normal(0, 0.8, size=(1, 11)), np.array([-10.0]), multi_class="multinomial")
+    orc, eng = _oracle(prob), _engine(prob, kernel=kernel)
+    np.random.seed(2)
+    want = orc.shap_values(prob["X"], nsamples=150, l1_reg=False)
+    got = eng.shap_values(prob["X"], nsamples=150, l1_reg=False, plans=[(Z, w) for (_, Z, w) in orc.plans])
+    for i in range(12):                      # class 1 (the small probability): the oracle's own 1 - x is exact there
+        assert rel_err(got[1][i], want[1][i]) < TOL
+    shared = eng.shap_values(prob["X"], nsamples=150, l1_reg=False)       # shared plan through the fast path
+    fx = prob["clf"].predict_proba(prob["X"])
+    np.testing.assert_allclose(shared[1].sum(1), np.log(fx[:, 1] / fx[:, 0]) - eng.expected_value[1], rtol=1e-8, atol=1e-8)
+    assert np.abs(shared[1]).max() > 0.1
