@@ -57,13 +57,13 @@ def workload(rank=0):
     return base
 
 
-def config_dict(world, kernel, plan_mode="shared"):
+def config_dict(world, kernel, plan_mode="shared", collective="none"):
     return {"workload": "Adult-shaped synthetic LR (BASELINE.json configs[1]): 2560 instances/GPU, D=49, 12 groups, "
                         "bg=100, nsamples=2048, l1_reg=False, logit link",
             "instances_per_gpu": N_INSTANCES, "global_instances": N_INSTANCES * world, "background": N_BACKGROUND,
             "nsamples": NSAMPLES, "features": 49, "groups": 12,
             "plan": "shared per M (seed 0)" if plan_mode == "shared" else "per instance, drawn on the GPU (Philox, seed 0)",
-            "parallelism": f"dp{world} (instances sharded, one all-gather of phi)", "kernel": kernel,
+            "parallelism": f"dp{world} (instances sharded, one all-gather of phi)", "collective": collective, "kernel": kernel,
             "l2_flush_between_steps": True}
 
 
@@ -223,11 +223,39 @@ def run_ours(args):
     phi_dev = torch.empty((C, n, G), dtype=torch.float64, device="cuda")
     phi_all = torch.empty((world, C, n, G), dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
+    # N > 1: the all-gather of phi is the engine's own push over NVLink peer memory (each rank stores its block into every
+    # peer's gathered buffer, then one cross-GPU barrier); NCCL all_gather_into_tensor if peer memory cannot be mapped
+    gather, collective = None, "none"
+    if world > 1:
+        collective = "nccl all_gather_into_tensor"
+        if os.environ.get("DKS_BENCH_NCCL", "0") != "1":
+            try:
+                gather = parallel.PeerGather(engine, C, n, G, torch.device("cuda", local_rank))
+                phi_dev = gather.local
+                collective = "push over peer memory (own kernel) + symmetric-memory barrier"
+            except Exception as exc:                      # pragma: no cover - depends on the box
+                print(f"[bench] peer-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
+                gather = None
+        flags = torch.tensor([1 if gather is not None else 0], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)      # all ranks or none
+        if int(flags.item()) == 0 and gather is not None:
+            gather.close()
+            gather, phi_dev, collective = None, torch.empty((C, n, G), dtype=torch.float64, device="cuda"), \
+                "nccl all_gather_into_tensor"
 
     def step_device():
         engine.explain_device(X_dev.data_ptr(), n, phi_dev.data_ptr(), nsamples=NSAMPLES)
-        if world > 1:
+        if gather is not None:
+            gather.barrier()
+        elif world > 1:
             dist.all_gather_into_tensor(phi_all, phi_dev)
+
+    if gather is not None:                                # once: the pushed result equals NCCL's
+        step_device()
+        torch.cuda.synchronize()
+        dist.all_gather_into_tensor(phi_all, phi_dev.contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(gather.buffer, phi_all), "peer-memory gather differs from all_gather_into_tensor"
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -334,7 +362,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 sigmoid/accumulate, f64 link + WLS", "data": "synthetic",
-            "config": config_dict(world, engine.kernel, args.plan_mode),
+            "config": config_dict(world, engine.kernel, args.plan_mode, collective),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

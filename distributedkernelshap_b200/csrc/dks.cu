@@ -815,6 +815,24 @@ int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev
     return DKS_OK;
 }
 
+// after the solve: this rank's phi goes to every peer's gathered buffer (no-op without dks_set_peers)
+static int launch_push(dks_ctx* ctx, const double* phi_dev) {
+    if (ctx->peer_world <= 1) return DKS_OK;
+    dks::PeerPush pp;
+    pp.npeers = 0;
+    for (int r = 0; r < ctx->peer_world; ++r) {
+        double* slab = ctx->peer_base[r] + (long long)ctx->peer_rank * ctx->peer_slab;
+        if (r == ctx->peer_rank && slab == phi_dev) continue;        // phi was written in place into the local slab
+        pp.dst[pp.npeers++] = slab;
+    }
+    if (pp.npeers == 0) return DKS_OK;
+    dim3 grid(8, pp.npeers);
+    dks::push_phi_kernel<<<grid, 256, 0, ctx->stream>>>(phi_dev, pp, ctx->peer_slab);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return DKS_OK;
+}
+
 static void drop_graph(dks_ctx* ctx) {
     if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
 }
@@ -849,6 +867,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
     const int64_t launches_before = ctx->launches;
     int rc = launch_prepare(ctx, X_dev, n);
     if (rc == DKS_OK) rc = launch_explain(ctx, phi_dev, nullptr, nullptr, 0);
+    if (rc == DKS_OK) rc = launch_push(ctx, phi_dev);
     if (capture) {
         ctx->capturing = false;
         cudaGraph_t graph = nullptr;
@@ -871,10 +890,25 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
             ctx->launches = launches_before;
             TRY(launch_prepare(ctx, X_dev, n));
             TRY(launch_explain(ctx, phi_dev, nullptr, nullptr, 0));
+            TRY(launch_push(ctx, phi_dev));
         }
     } else if (rc != DKS_OK) {
         return rc;
     }
+    return DKS_OK;
+}
+
+int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_ptrs_host, int64_t slab_doubles) {
+    REQUIRE(ctx, "dks_set_peers: ctx is NULL");
+    ctx->epoch++;
+    if (world <= 1 || gathered_ptrs_host == nullptr) { ctx->peer_world = 0; return DKS_OK; }
+    REQUIRE(world <= 16 && rank >= 0 && rank < world && slab_doubles > 0, "dks_set_peers: bad arguments (at most 16 ranks)");
+    for (int r = 0; r < world; ++r) {
+        REQUIRE(gathered_ptrs_host[r] != 0 && (gathered_ptrs_host[r] & 15) == 0, "dks_set_peers: peer buffers must be 16-byte aligned");
+        ctx->peer_base[r] = reinterpret_cast<double*>(gathered_ptrs_host[r]);
+    }
+    REQUIRE((slab_doubles & 1) == 0, "dks_set_peers: slab size must be even (128-bit stores)");
+    ctx->peer_world = world; ctx->peer_rank = rank; ctx->peer_slab = slab_doubles;
     return DKS_OK;
 }
 

@@ -181,6 +181,12 @@ struct dks_ctx {
     int64_t graph_launches = 0;
     int64_t graph_kernels = 0;    // kernels one replay of the captured graph launches
 
+    // push all-gather over peer memory: after a device-resident explain, phi is stored into slab `peer_rank` of every
+    // peer's gathered buffer (dks_set_peers)
+    int peer_world = 0, peer_rank = 0;
+    long long peer_slab = 0;                       // doubles per slab
+    double* peer_base[16] = {};                    // device pointers to each rank's [world][slab] buffer
+
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
 };

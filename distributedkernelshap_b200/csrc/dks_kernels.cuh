@@ -488,6 +488,18 @@ __global__ void plan_factor_wide_kernel(const uint64_t* __restrict__ z, const do
     if (threadIdx.x == 0 && !s_ok) { status[0] = DKS_ERR_NUMERIC; status[1] = M; }
 }
 
+// Push all-gather: every rank stores its block of phi into slab `rank` of each peer's gathered buffer through NVLink
+// peer memory (128-bit stores; blockIdx.y = peer slot).  The caller follows up with a cross-GPU barrier.
+struct PeerPush { double* dst[16]; int npeers; };
+__global__ void push_phi_kernel(const double* __restrict__ src, PeerPush pp, long long n_doubles) {
+    double* dst = pp.dst[blockIdx.y];
+    const long long nvec = n_doubles >> 1;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) d2[i] = s2[i];
+    if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n_doubles - 1] = src[n_doubles - 1];
+}
+
 // an instance list that must be empty (shapes no kernel covers): report instead of computing
 __global__ void flag_unsupported_kernel(const int* __restrict__ count, int detail, int* __restrict__ status) {
     if (*count > 0 && atomicCAS(&status[0], 0, DKS_ERR_UNSUPPORTED) == 0) status[1] = detail;

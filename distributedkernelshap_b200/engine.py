@@ -324,6 +324,16 @@ class GpuKernelExplainer:
         self._set_nsamples(nsamples)
         _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n), C.c_void_p(int(phi_dev_ptr))))
 
+    def set_peers(self, world, rank, gathered_ptrs, slab_doubles):
+        """Multi-GPU push all-gather: ``gathered_ptrs[r]`` = device address (mapped in this process) of rank r's gathered
+        ``[world, C, n, G]`` buffer; after every ``explain_device`` this rank's phi is stored into slab ``rank`` of every
+        peer's buffer by the engine's own kernel.  ``world <= 1`` switches it off."""
+        if world <= 1:
+            _cabi.check(self.lib.dks_set_peers(self._ctx, 0, 0, None, 0))
+            return
+        ptrs = np.asarray([int(p) for p in gathered_ptrs], dtype=np.uint64)
+        _cabi.check(self.lib.dks_set_peers(self._ctx, int(world), int(rank), _cabi.ptr(ptrs), int(slab_doubles)))
+
     def graph_launches(self):
         """How many ``explain_device`` calls were replayed as one CUDA-graph launch."""
         cnt = C.c_int64(0)

@@ -79,3 +79,31 @@ def allgather_rows(local, counts):
     dist.all_gather_into_tensor(recv, send.view(-1))
     recv = recv.view(world, C, pad, G).cpu().numpy()
     return np.concatenate([recv[r][:, :counts[r]] for r in range(world)], axis=1)
+
+
+class PeerGather:
+    """Gathered ``[world, C, n, G]`` float64 buffer in symmetric (peer-mapped) memory, one per rank.
+
+    The engine stores its block of phi into slab ``rank`` of every peer's buffer with its own kernel over NVLink peer
+    memory (``engine.set_peers`` / ``dks_set_peers``); ``barrier()`` is the cross-GPU signal exchange that makes the
+    gathered buffer complete on every rank.  torch only allocates and maps the memory
+    (``torch.distributed._symmetric_memory``).  Raises if the process group / driver cannot provide peer mappings: callers
+    fall back to ``all_gather_into_tensor``."""
+
+    def __init__(self, engine, C, n, G, device):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        dist = _dist()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.buffer = symm_mem.empty((self.world, C, n, G), dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.local = self.buffer[self.rank]                       # the solve writes this slab in place
+        self.engine = engine
+        engine.set_peers(self.world, self.rank, ptrs, C * n * G)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+    def close(self):
+        self.engine.set_peers(0, 0, None, 0)

@@ -138,6 +138,12 @@ int dks_explain_dev(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_zbits_dev
  * Asynchronous like dks_explain_dev; dks_last_timings keeps working (external event-record nodes). */
 int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev);
 int dks_graph_launches(dks_ctx* ctx, int64_t* count);
+/* Multi-GPU, one process per GPU: gathered_ptrs_host[r] is the device address, valid in THIS process (peer mapping, e.g.
+ * torch symmetric memory), of rank r's gathered buffer [world][slab_doubles].  After every dks_run_dev the engine stores
+ * its phi into slab `rank` of every peer's buffer with its own kernel over NVLink peer memory -- the all-gather of the
+ * reference's result collection (distributed.py:156-179) without NCCL; the caller completes it with a cross-GPU barrier.
+ * Pass phi_dev = own buffer + rank * slab_doubles to have the solve write the local slab in place.  world <= 1 clears. */
+int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_ptrs_host, int64_t slab_doubles);
 /* convenience: prepare + explain from/to host memory; H2D, kernels, D2H; synchronises.  This is the call a
  * non-torch host (ctypes / cgo) makes and the one bench.py's end-to-end number goes through. */
 int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
