@@ -228,7 +228,11 @@ def run_ours(args):
     gather, collective = None, "none"
     if world > 1:
         collective = "nccl all_gather_into_tensor"
-        if os.environ.get("DKS_BENCH_NCCL", "0") != "1":
+        # measured on this pool (profiles/r1_bench_*gpu_{push,nccl}.log, ms/step push vs NCCL): N=2 0.224 / 0.221,
+        # N=4 0.229 / 0.308, N=8 0.344 / 0.240 (NCCL's in-switch path wins there): push up to 4 ranks, NCCL beyond.
+        # DKS_BENCH_NCCL=1 / DKS_BENCH_PUSH=1 force one or the other.
+        use_push = (world <= 4 or os.environ.get("DKS_BENCH_PUSH", "0") == "1") and os.environ.get("DKS_BENCH_NCCL", "0") != "1"
+        if use_push:
             try:
                 gather = parallel.PeerGather(engine, C, n, G, torch.device("cuda", local_rank))
                 phi_dev = gather.local
