@@ -64,7 +64,7 @@ SIGNATURES = {
     "dks_run_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dks_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "dks_graph_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
-    "dks_get_link_fx": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dks_get_link_fx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dks_get_varying": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dks_explain_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dks_explain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

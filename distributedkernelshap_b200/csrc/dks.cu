@@ -798,9 +798,10 @@ int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host) {
     return DKS_OK;
 }
 
-int dks_get_link_fx(dks_ctx* ctx, double* out_host) {
+int dks_get_link_fx(dks_ctx* ctx, double* out_host, int n) {
     BIND(ctx);
     REQUIRE(ctx->prepared && out_host, "dks_get_link_fx: call dks_prepare_* / dks_explain_* first");
+    REQUIRE(n == ctx->cur_n, "dks_get_link_fx: the last stage 1 ran over %d rows, the caller expects %d", ctx->cur_n, n);
     const size_t cnt = (size_t)ctx->cur_n * ctx->C;
     CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_dlink, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

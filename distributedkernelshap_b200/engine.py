@@ -97,6 +97,8 @@ class GpuKernelExplainer:
         self.fnull = fnull
         self.expected_value = expected if self.vector_out else float(expected[0])
         self._nsamples_req = None
+        self._link_fx_parts = []
+        self._last_rows = 0
         self._check_model_against_callable(bg)
 
     # ------------------------------------------------------------------------------------------------------
@@ -280,9 +282,14 @@ class GpuKernelExplainer:
         the predictor over ``X`` again for ``raw_prediction`` (kernel_shap.py:949)."""
         if self._link_fx_parts:                 # the call went through in row chunks
             out = np.concatenate(self._link_fx_parts, axis=0)
+        elif self._last_rows == 0:
+            return None
         else:
             out = np.zeros((self._last_rows, self.D))
-            _cabi.check(self.lib.dks_get_link_fx(self._ctx, _cabi.ptr(out)))
+            rc = self.lib.dks_get_link_fx(self._ctx, _cabi.ptr(out), self._last_rows)
+            if rc == _cabi.DKS_ERR_INVALID:     # another call (varying(), explain_device()) ran stage 1 since
+                return None
+            _cabi.check(rc)
         return out if self.vector_out else out[:, 0]
 
     def instance_plans(self):

@@ -121,7 +121,7 @@ int dks_prepare_dev(dks_ctx* ctx, const double* X_dev, int n);
 int dks_get_m_histogram(dks_ctx* ctx, int32_t* hist_host);
 /* after prepare / explain: link(f(x)) per instance and output, [n][C] -- what KernelShap.build_explanation stores as
  * `raw_prediction` (kernel_shap.py:949 runs the predictor over X a second time for it); synchronises. */
-int dks_get_link_fx(dks_ctx* ctx, double* out_host);
+int dks_get_link_fx(dks_ctx* ctx, double* out_host, int n /* rows the caller's buffer holds: must match */);
 /* after prepare: per-instance M and varying bit-mask (debug / tests); synchronises. */
 int dks_get_varying(dks_ctx* ctx, int32_t* M_host, uint64_t* mask_host);
 
