@@ -4,9 +4,12 @@
 // Adult-shaped data every instance has M = G), the masked score separates:
 //     t(i, s, j) = a(i, s) + d(s, j),   a(i, s) = scale * sum_k z_sk XW_i[k],   d(s, j) = scale * (score_j - sum_k z_sk BW[j][k])
 // so  2^t = A(i, s) * Dm(s, j)  with Dm = 2^d independent of the instance.  Dm (S x N floats, 0.8 MB for Adult) is
-// computed once per plan; every lane keeps its coalition row of Dm in REGISTERS and streams ~n/27 instances through it:
-// per element one FMUL instead of a GEMM + EX2, and with the paired reciprocal 0.5 MUFU op.  Output: (sum p1, sum p0)
-// per (instance, coalition); wls_shared_kernel applies the link and solves with the plan's precomputed inverse.
+// computed once per plan, row-normalised; a warp owns 32 coalition rows and streams the instances through them.  Two
+// elements share a reciprocal,  p1a + p1b = (2 + sm) / (1 + sm + q),  sm = A (Dma + Dmb),  q = A^2 (Dma Dmb),  so what the
+// kernel keeps per row are the pair sums and pair products of Dm -- in TENSOR MEMORY (explain_shared_tmem_kernel, the
+// default) or, in the first version kept for comparisons, the raw row in registers (explain_shared_kernel,
+// DKS_SHARED_DM=regs).  No GEMM, no EX2 per element: 3.5 packed-fp32 lane-ops + 0.5 MUFU.  Output: (sum p1, sum p0) per
+// (instance, coalition); wls_pmat_kernel / wls_shared_kernel apply the link and solve with what the plan precomputed.
 // Instances with a partial varying set, per-instance plans and other heads go through the general kernels.
 #pragma once
 
@@ -16,7 +19,7 @@
 namespace dks {
 namespace shared_path {
 
-constexpr int MAXN = 128;            // background rows held in registers per lane
+constexpr int MAXN = 128;            // background rows per launch (a warp's slice of tensor memory / a lane's registers)
 constexpr int WARPS_PER_CTA = 12;
 constexpr float U_CLAMP = 1.152921504606846976e18f;   // 2^60: (1 + ua)(1 + ub) stays finite in fp32
 
