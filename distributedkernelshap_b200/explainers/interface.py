@@ -8,111 +8,100 @@ import copy
 import json
 import logging
 import pprint
-from collections import ChainMap
+import warnings
 from typing import Any
 
 import numpy as np
 
 logger = logging.getLogger(__name__)
 
-DEFAULT_META_KERNEL_SHAP = {
-    "name": None,
-    "type": ["blackbox"],
-    "task": None,
-    "explanations": ["local", "global"],
-    "params": {},
-}  # type: dict
 
-DEFAULT_DATA_KERNEL_SHAP = {
-    "shap_values": [],
-    "expected_value": [],
-    "link": "identity",
-    "categorical_names": {},
-    "feature_names": [],
-    "raw": {
-        "raw_prediction": None,
-        "prediction": None,
-        "instances": None,
-        "importances": {},
-    },
-}  # type: dict
-
-DEFAULT_META = {
-    "name": None,
-    "type": [],
-    "explanations": [],
-    "params": {},
-}  # type: dict
+def _meta_template(kinds=(), scopes=(), with_task=False):
+    out = {"name": None, "type": list(kinds)}
+    if with_task:
+        out["task"] = None
+    out.update(explanations=list(scopes), params={})
+    return out
 
 
-class Explainer(abc.ABC):
+# what an explainer / an explanation starts from (keys as in the reference, interface.py:14-37)
+DEFAULT_META = _meta_template()
+DEFAULT_META_KERNEL_SHAP = _meta_template(kinds=("blackbox",), scopes=("local", "global"), with_task=True)
+DEFAULT_DATA_KERNEL_SHAP = dict(
+    shap_values=[], expected_value=[], link="identity", categorical_names={}, feature_names=[],
+    raw=dict(raw_prediction=None, prediction=None, instances=None, importances={}),
+)
+
+
+class _KeysAsAttributes:
+    """Mixin: every key of the given dictionaries becomes an attribute (meta keys win over data keys)."""
+
+    def _expose(self, *dicts):
+        for d in reversed(dicts):
+            for key, value in d.items():
+                setattr(self, key, value)
+
+
+class Explainer(_KeysAsAttributes, abc.ABC):
     """Base class for explainer algorithms: carries a ``meta`` dict whose keys are also exposed as attributes."""
 
     def __init__(self, meta: dict = None):
-        self.meta = copy.deepcopy(DEFAULT_META) if meta is None else meta
-        self.meta["name"] = self.__class__.__name__
-        for key, value in self.meta.items():
-            setattr(self, key, value)
+        self.meta = meta if meta is not None else copy.deepcopy(DEFAULT_META)
+        self.meta["name"] = type(self).__name__
+        self._expose(self.meta)
 
     def __repr__(self):
-        return f"{self.__class__.__name__}(meta={pprint.pformat(self.meta)})"
+        return "{}(meta={})".format(type(self).__name__, pprint.pformat(self.meta))
 
     @abc.abstractmethod
     def explain(self, X: Any) -> "Explanation":
-        pass
+        """Explain the rows of ``X``."""
 
 
 class FitMixin(abc.ABC):
     @abc.abstractmethod
     def fit(self, X: Any) -> "Explainer":
-        pass
+        """Fit the explainer on background data."""
 
 
-class Explanation:
+class Explanation(_KeysAsAttributes):
     """Explanation returned by explainers: ``meta`` and ``data`` dicts, keys exposed as attributes."""
 
     def __init__(self, meta: dict, data: dict):
-        self.meta = meta
-        self.data = data
-        for key, value in ChainMap(self.meta, self.data).items():
-            setattr(self, key, value)
+        self.meta, self.data = meta, data
+        self._expose(meta, data)
 
     def __repr__(self):
-        return f"Explanation(meta={pprint.pformat(self.meta)}, data={pprint.pformat(self.data)})"
+        return "Explanation(meta={}, data={})".format(pprint.pformat(self.meta), pprint.pformat(self.data))
 
     def to_json(self) -> str:
-        """Serialize the explanation data and metadata into a json format."""
-        return json.dumps({"meta": self.meta, "data": self.data}, cls=NumpyEncoder)
+        """The explanation (meta + data) as a JSON string; NumPy scalars and arrays become plain numbers and lists."""
+        return json.dumps(dict(meta=self.meta, data=self.data), cls=NumpyEncoder)
 
     @classmethod
     def from_json(cls, jsonrepr) -> "Explanation":
-        """Create an Explanation from its json representation."""
-        dictrepr = json.loads(jsonrepr)
-        try:
-            meta = dictrepr["meta"]
-            data = dictrepr["data"]
-        except KeyError:
-            logger.exception("Invalid explanation representation")
-            raise
-        return cls(meta=meta, data=data)
+        """Inverse of ``to_json`` (arrays come back as lists)."""
+        parsed = json.loads(jsonrepr)
+        missing = [k for k in ("meta", "data") if k not in parsed]
+        if missing:
+            logger.error("Invalid explanation representation: no %s", missing)
+            raise KeyError(missing[0])
+        return cls(meta=parsed["meta"], data=parsed["data"])
 
     def __getitem__(self, item):
-        """Deprecated dictionary-style access, kept because the reference keeps it."""
-        import warnings
-        msg = "The Explanation object is not a dictionary anymore and accessing elements should " \
-              "be done via attribute access. Accessing via item will stop working in a future version."
-        warnings.warn(msg, DeprecationWarning, stacklevel=2)
+        """Dictionary-style access, deprecated in the reference and kept the same way here."""
+        warnings.warn("Explanation objects are not dictionaries: read '{}' as an attribute; item access will be removed "
+                      "in a future version.".format(item), DeprecationWarning, stacklevel=2)
         return getattr(self, item)
 
 
 class NumpyEncoder(json.JSONEncoder):
+    """JSON encoder that understands NumPy scalars and arrays."""
+
+    _CASTS = ((np.bool_, bool), (np.integer, int), (np.floating, float), (np.ndarray, np.ndarray.tolist))
+
     def default(self, obj):
-        if isinstance(obj, np.integer):
-            return int(obj)
-        if isinstance(obj, np.floating):
-            return float(obj)
-        if isinstance(obj, np.bool_):
-            return bool(obj)
-        if isinstance(obj, np.ndarray):
-            return obj.tolist()
-        return json.JSONEncoder.default(self, obj)
+        for numpy_type, cast in self._CASTS:
+            if isinstance(obj, numpy_type):
+                return cast(obj)
+        return super().default(obj)

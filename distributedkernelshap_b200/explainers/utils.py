@@ -16,41 +16,39 @@ MODEL_LOCAL = 'assets/predictor.pkl'
 
 
 class Bunch(dict):
-    """Dictionary whose keys are also attributes."""
+    """Dictionary whose keys can also be read and written as attributes (the container the reference's data pickles hold)."""
 
-    def __init__(self, **kwargs):
-        super().__init__(kwargs)
+    def __init__(self, **fields):
+        dict.__init__(self, fields)
 
-    def __setattr__(self, key, value):
-        self[key] = value
+    def __getattr__(self, name):
+        if name in self:
+            return self[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
 
     def __dir__(self):
-        return self.keys()
-
-    def __getattr__(self, key):
-        try:
-            return self[key]
-        except KeyError:
-            raise AttributeError(key)
+        return list(self.keys())
 
 
 def methdispatch(func: Callable):
-    """``functools.singledispatch`` for methods: dispatches on the type of the first argument after ``self``."""
-    dispatcher = singledispatch(func)
+    """``functools.singledispatch`` for methods: the implementation is chosen by the type of the first argument after
+    ``self``."""
+    registry = singledispatch(func)
 
-    def wrapper(*args, **kw):
-        return dispatcher.dispatch(args[1].__class__)(*args, **kw)
+    def dispatching_method(self, arg, *rest, **kwargs):
+        return registry.dispatch(type(arg))(self, arg, *rest, **kwargs)
 
-    wrapper.register = dispatcher.register
-    update_wrapper(wrapper, dispatcher)
-    return wrapper
+    dispatching_method.register = registry.register
+    return update_wrapper(dispatching_method, registry)
 
 
 def get_filename(workers: int, batch_size: int, cpu_fraction: float = 1.0, serve: bool = True):
-    """Result file name of an experiment (same convention as the reference, so its notebooks can read them)."""
-    if serve:
-        return f"results/ray_replicas_{workers}_maxbatch_{batch_size}_actorfr_{cpu_fraction}.pkl"
-    return f"results/ray_workers_{workers}_bsize_{batch_size}_actorfr_{cpu_fraction}.pkl"
+    """Result-file name under ``results/`` for an experiment configuration (same scheme as the reference)."""
+    stem = "ray_replicas_{}_maxbatch_{}" if serve else "ray_workers_{}_bsize_{}"
+    return ("results/" + stem + "_actorfr_{}.pkl").format(workers, batch_size, cpu_fraction)
 
 
 def batch_slices(n_records: int, batch_size: int = None, n_batches: int = 4) -> List[slice]:
@@ -85,12 +83,12 @@ def load_model(path: str = MODEL_LOCAL):
 def load_data():
     """The reference's Adult pickles if present (``data/adult_*.pkl``), else the synthetic stand-in with the same
     dictionary structure (``data['all']['groups']``, ``data['background']['X']['preprocessed']``, ...)."""
-    if os.path.exists(BACKGROUND_SET_LOCAL) and os.path.exists(EXPLANATIONS_SET_LOCAL):
-        data = {}
-        with open(BACKGROUND_SET_LOCAL, 'rb') as f:
-            data['background'] = pickle.load(f)
-        with open(EXPLANATIONS_SET_LOCAL, 'rb') as f:
-            data['all'] = pickle.load(f)
-        return data
+    sources = {"background": BACKGROUND_SET_LOCAL, "all": EXPLANATIONS_SET_LOCAL}
+    if all(os.path.exists(path) for path in sources.values()):
+        loaded = {}
+        for key, path in sources.items():
+            with open(path, "rb") as handle:
+                loaded[key] = pickle.load(handle)
+        return loaded
     from distributedkernelshap_b200.datasets import adult_like
     return adult_like()["data"]
