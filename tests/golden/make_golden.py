@@ -50,7 +50,25 @@ def make(name, seed, widths, n, N, link, kappa, nsamples, full, weights):
                         expected_value=orc.expected_value)
 
 
+def make_device_plan_fixture(name, cases):
+    """Plans of the device-side sampler (csrc/dks_sampler.cuh) as the sequential loop builds them from the Philox stream
+    (tests/sampler_twin.py): the GPU test compares the kernel's output with these committed arrays as well."""
+    from oracle.shap_kernel_oracle import build_plan, effective_nsamples
+    from sampler_twin import PhiloxPlanStream
+    from distributedkernelshap_b200.plan import pack_dense_plan
+    out = {}
+    for k, (M, nsamples, seed, row) in enumerate(cases):
+        S, _ = effective_nsamples(M, nsamples)
+        Z, w, _ = build_plan(M, S, rng=PhiloxPlanStream(seed, row))
+        out[f"case{k}"] = np.array([M, S, seed, row], dtype=np.int64)
+        out[f"zbits{k}"] = pack_dense_plan(Z)
+        out[f"w{k}"] = w
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
+    make_device_plan_fixture("device_plans_philox", [(12, 300, 77, 0), (12, 300, 77, 5), (6, 40, 77, 3), (9, 120, 77, 11),
+                                                     (20, 2088, 77, 2)])
     make("full_logit_m7", 101, (1, 2, 1, 1, 3, 1, 2), n=6, N=9, link="logit", kappa=2.0, nsamples=126, full=True, weights=True)
     make("full_identity_m6", 102, (1, 1, 2, 1, 4, 1), n=5, N=8, link="identity", kappa=1.0, nsamples=62, full=True, weights=False)
     make("sampled_logit_m12", 103, (1, 1, 1, 1, 3, 2, 1, 2, 1, 4, 1, 1), n=8, N=20, link="logit", kappa=2.0, nsamples=400,

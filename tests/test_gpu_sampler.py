@@ -16,6 +16,17 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+def _fixture_plans():
+    """(M, S, seed, row) -> (zbits, w) from tests/golden/device_plans_philox.npz."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_plans_philox.npz"))
+    out, k = {}, 0
+    while f"case{k}" in fx:
+        out[tuple(int(v) for v in fx[f"case{k}"])] = (fx[f"zbits{k}"], fx[f"w{k}"])
+        k += 1
+    return out
+
+
 def _expected_plan(M, nsamples, seed, row):
     from oracle.shap_kernel_oracle import build_plan
     from distributedkernelshap_b200.plan import pack_dense_plan, resolve_nsamples
@@ -46,6 +57,10 @@ def test_device_plans_equal_the_sequential_loop_on_the_same_stream(widths, nsamp
         np.testing.assert_array_equal(zb[i, :S], want_z, err_msg=f"instance {i}")
         np.testing.assert_allclose(w[i, :S], want_w, rtol=1e-13, atol=0)
         assert np.all(w[i, S:] == 0)
+        committed = _fixture_plans().get((int(M), S, 77, i))          # the same plan as a committed golden array
+        if committed is not None:
+            np.testing.assert_array_equal(zb[i, :S], committed[0])
+            np.testing.assert_allclose(w[i, :S], committed[1], rtol=1e-13, atol=0)
         # the regression prepared with the plan (normal matrix from popcounts of the bit-transposed rows, factored in
         # the sampler kernel) must give the oracle's phi for that plan
         k = np.arange(int(M), dtype=np.uint64)

@@ -79,3 +79,22 @@ def test_wide_plans_two_words_match_the_oracle():
         np.testing.assert_allclose(plan.weights, w, rtol=1e-14)
     with pytest.raises(ValueError):
         build_plan(129, 100)
+
+
+def test_device_plan_fixture_is_reproduced_by_the_twin():
+    """tests/golden/device_plans_philox.npz pins the Philox stream adapter + sequential loop (what the GPU sampler must
+    reproduce) independently of the code that generated it."""
+    import os
+    from oracle.shap_kernel_oracle import build_plan as oracle_build_plan
+    from sampler_twin import PhiloxPlanStream
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_plans_philox.npz"))
+    k = 0
+    while f"case{k}" in fx:
+        M, S, seed, row = (int(v) for v in fx[f"case{k}"])
+        Z, w, _ = oracle_build_plan(M, S, rng=PhiloxPlanStream(seed, row))
+        np.testing.assert_array_equal(pack_dense_plan(Z), fx[f"zbits{k}"])
+        np.testing.assert_allclose(w, fx[f"w{k}"], rtol=1e-15)
+        plan = build_plan(M, S, rng=PhiloxPlanStream(seed, row))        # the product's builder on the same stream
+        np.testing.assert_array_equal(plan.zbits, fx[f"zbits{k}"])
+        k += 1
+    assert k == 5
