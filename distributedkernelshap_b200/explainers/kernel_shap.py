@@ -459,7 +459,9 @@ class KernelShap(Explainer, FitMixin):
 
         X = X.toarray() if (isinstance(X, sparse.spmatrix) or sparse.issparse(X)) else np.array(X)
 
-        data = copy.deepcopy(DEFAULT_DATA_KERNEL_SHAP)
+        data = {key: (dict(value) if isinstance(value, dict) else copy.copy(value))      # fresh containers, two levels deep
+                for key, value in DEFAULT_DATA_KERNEL_SHAP.items()}
+        data['raw']['importances'] = {}
         data.update(
             shap_values=shap_values,
             expected_value=np.array(expected_value),
