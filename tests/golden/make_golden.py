@@ -63,7 +63,7 @@ def make_device_plan_fixture(name, cases):
         out[f"case{k}"] = np.array([M, S, seed, row], dtype=np.int64)
         out[f"zbits{k}"] = pack_dense_plan(Z)
         out[f"w{k}"] = w
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "plans", name + ".npz"), **out)
 
 
 if __name__ == "__main__":

@@ -17,9 +17,9 @@ TOL = 1e-5
 
 
 def _fixture_plans():
-    """(M, S, seed, row) -> (zbits, w) from tests/golden/device_plans_philox.npz."""
+    """(M, S, seed, row) -> (zbits, w) from tests/golden/plans/device_plans_philox.npz."""
     import os
-    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_plans_philox.npz"))
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "plans", "device_plans_philox.npz"))
     out, k = {}, 0
     while f"case{k}" in fx:
         out[tuple(int(v) for v in fx[f"case{k}"])] = (fx[f"zbits{k}"], fx[f"w{k}"])

@@ -82,12 +82,12 @@ def test_wide_plans_two_words_match_the_oracle():
 
 
 def test_device_plan_fixture_is_reproduced_by_the_twin():
-    """tests/golden/device_plans_philox.npz pins the Philox stream adapter + sequential loop (what the GPU sampler must
+    """tests/golden/plans/device_plans_philox.npz pins the Philox stream adapter + sequential loop (what the GPU sampler must
     reproduce) independently of the code that generated it."""
     import os
     from oracle.shap_kernel_oracle import build_plan as oracle_build_plan
     from sampler_twin import PhiloxPlanStream
-    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_plans_philox.npz"))
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "plans", "device_plans_philox.npz"))
     k = 0
     while f"case{k}" in fx:
         M, S, seed, row = (int(v) for v in fx[f"case{k}"])
