@@ -29,7 +29,12 @@ if REPO not in sys.path:
 N_INSTANCES = 2560
 N_BACKGROUND = 100
 NSAMPLES = 2048
-METRIC = "instances explained/sec (bg=100, nsamples=2048)"
+METRIC = "instances explained/sec (bg=100, nsamples=2048) at 1/2/4/8 B200 vs ray CPU"
+try:                                               # BASELINE.json's metric string, verbatim
+    with open(os.path.join(REPO, "BASELINE.json")) as _f:
+        METRIC = json.load(_f).get("metric", METRIC)
+except (OSError, ValueError):
+    pass
 
 
 def parse_args():
