@@ -20,7 +20,14 @@ import statistics
 import sys
 import time
 
-import numpy as np
+# One BLAS/OpenMP thread per process, set BEFORE NumPy is imported anywhere (this process and every spawned worker
+# re-import this module, so they inherit it): a CPU worker stands for one single-CPU ray actor (distributed.py:125),
+# and N workers with full-width BLAS pools would oversubscribe the host.  torchrun exports OMP_NUM_THREADS=1 itself;
+# a plain `python bench.py` now behaves the same.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"
+
+import numpy as np  # noqa: E402
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
@@ -75,30 +82,67 @@ def config_dict(world, kernel, plan_mode="shared", collective="none"):
 # ------------------------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    """Explain a slice of instances with the oracle in a single-threaded worker (one ray actor = one CPU)."""
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    lo, hi = args
+_CPU = {}
+
+
+def _cpu_init():
+    """Once per worker process: pin BLAS to one thread (belt and braces on top of the environment), build the workload
+    and the explainer replica -- what a ray actor does in its constructor (kernel_shap.py:225-229), outside every timed
+    region."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["limits"] = threadpool_limits(limits=1)
+    except Exception:                                  # pragma: no cover - threadpoolctl is optional
+        pass
     from oracle.shap_kernel_oracle import DenseData, KernelExplainerWrapperOracle
     wl = workload()
     dd = DenseData(wl["background"], wl["group_names"], wl["groups"])
-    expl = KernelExplainerWrapperOracle(wl["predictor"].predict_proba, dd, link="logit", seed=0, faithful_run=True)
+    _CPU["X"] = wl["X_explain"]
+    _CPU["explainer"] = KernelExplainerWrapperOracle(wl["predictor"].predict_proba, dd, link="logit", seed=0,
+                                                     faithful_run=True)
+
+
+def _cpu_worker(args):
+    """Explain a slice of instances with the oracle in a single-threaded worker (one ray actor = one CPU); a fresh
+    coalition plan per instance from the worker's own MT19937 stream, like the reference.  Returns the explain time."""
+    if "explainer" not in _CPU:
+        _cpu_init()
+    lo, hi = args
     t0 = time.perf_counter()
-    expl.get_explanation(wl["X_explain"][lo:hi], nsamples=NSAMPLES, l1_reg=False, silent=True)
+    _CPU["explainer"].get_explanation(_CPU["X"][lo:hi], nsamples=NSAMPLES, l1_reg=False, silent=True)
     return time.perf_counter() - t0
 
 
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(m.get("num_threads", 1)) for m in threadpool_info()] + [1])
+    except Exception:                                  # pragma: no cover
+        return None
+
+
 def cpu_baseline_single(sample):
-    """One worker, `sample` instances (== reference `--workers 1`; ~0.6 s per instance)."""
+    """One worker, `sample` instances (== reference `--workers 1`; ~0.4 s per instance)."""
     t = _cpu_worker((0, sample))
-    return {"value": sample / t, "unit": "instances/s", "cores": 1, "kind": "port",
+    return {"value": sample / t, "unit": "instances/s", "cores": 1, "kind": "port", "blas_threads": _blas_threads(),
             "sample": f"first {sample} of the 2560 instances, oracle/shap_kernel_oracle.py (NumPy restatement of "
-                      f"shap 0.35.0 KernelExplainer, interpreted S x N reduction loop kept), 1 process, {t:.1f} s"}
+                      f"shap 0.35.0 KernelExplainer, interpreted S x N reduction loop kept, a fresh plan per instance), "
+                      f"1 process, 1 BLAS thread, {t:.1f} s"}
+
+
+def reference_config(cores, per_worker):
+    return {"workload": "Adult-shaped synthetic LR (BASELINE.json configs[1]): D=49, 12 groups, bg=100, nsamples=2048, "
+                        "l1_reg=False, logit link",
+            "instances_per_step": cores * per_worker, "background": N_BACKGROUND, "nsamples": NSAMPLES, "features": 49,
+            "groups": 12, "plan": "per instance (MT19937 stream of each worker, like shap)",
+            "parallelism": f"{cores} single-threaded worker processes x {per_worker} instances (the ray ActorPool of "
+                           "distributed.py:125 without ray)", "kernel": "cpu-oracle"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; shap/ray are not installable offline) on all host
-    cores, one single-threaded worker process per core like the ray ActorPool (distributed.py:125)."""
+    cores, one single-threaded worker process per core like the ray ActorPool (distributed.py:125).  Workers build
+    their explainer replica once (pool initializer); a step is one pool.map over `cores` slices, wall-clock timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -107,23 +151,26 @@ def run_reference(args):
     per_worker = 2
     ctx = mp.get_context("spawn")
     times = []
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * cores)            # every worker is up and has imported/built everything
         for step in range(args.warmup + args.steps):
             chunks = [(w * per_worker, (w + 1) * per_worker) for w in range(cores)]
             t0 = time.perf_counter()
-            pool.map(_cpu_worker, chunks)
+            pool.map(_cpu_worker, chunks, chunksize=1)
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append(dt)
     per_step = cores * per_worker
     ms = 1e3 * sum(times) / len(times)
     value = per_step / (ms / 1e3)
-    sample = (f"{per_step} instances per step ({per_worker} per worker process x {cores} single-threaded workers) of the "
-              "Adult-shaped workload; oracle port of shap 0.35.0 (faithful interpreted reduction loop)")
+    sample = (f"{per_step} instances per step ({per_worker} per worker process x {cores} single-threaded workers, BLAS "
+              f"pinned to 1 thread before NumPy loads) of the Adult-shaped workload; oracle port of shap 0.35.0 (faithful "
+              "interpreted reduction loop, a fresh plan per instance)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(1, "cpu-oracle"),
-            "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": reference_config(cores, per_worker),
+            "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample,
+                             "blas_threads": _blas_threads()},
             "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -50,6 +50,19 @@ void dev_free(T** p) {
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
+// frees the device buffers the plan of one M owns (all M when M < 0); the caller has synchronised the stream
+void free_plan_allocs(dks_ctx* ctx, int M) {
+    for (int m = 0; m <= DKS_MAX_GROUPS; ++m) {
+        if (M >= 0 && m != M) continue;
+        for (void* q : ctx->plan_allocs[m]) cudaFree(q);
+        ctx->plan_allocs[m].clear();
+    }
+}
+bool any_plan_allocs(const dks_ctx* ctx) {
+    for (int m = 0; m <= DKS_MAX_GROUPS; ++m) if (!ctx->plan_allocs[m].empty()) return true;
+    return false;
+}
+
 int bind(dks_ctx* ctx) {
     if (!ctx) return fail(DKS_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -387,7 +400,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
-    for (void* p : ctx->plan_allocs) cudaFree(p);
+    free_plan_allocs(ctx, -1);
     dks::tc_release(ctx);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -542,9 +555,8 @@ int dks_fit(dks_ctx* ctx) {
     CUDA_TRY(cudaStreamSynchronize(st));
     ctx->cap_n = 0;  // workspace shapes depend on G, R, C
     ctx->prepared = false;
-    if (!ctx->plan_allocs.empty()) {   // plans carry tables derived from the background/model: drop them
-        for (void* q : ctx->plan_allocs) cudaFree(q);
-        ctx->plan_allocs.clear();
+    if (any_plan_allocs(ctx)) {   // plans carry tables derived from the background/model: drop them
+        free_plan_allocs(ctx, -1);
         memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
         ctx->max_plan_S = 0;
         CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
@@ -608,6 +620,14 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_shared_plan: M=%d out of [2,%d]", M, DKS_MAX_GROUPS);
     REQUIRE(S >= 1 && zbits_host && w_host, "dks_set_shared_plan: bad arguments");
     uint64_t* dz = nullptr; double* dw = nullptr; double* dc = nullptr; double* di = nullptr;
+    if (!ctx->plan_allocs[M].empty()) {
+        // replacing the plan of this M (another nsamples): nothing in flight may still read the old buffers
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        free_plan_allocs(ctx, M);
+        memset(&ctx->h_plans[M], 0, sizeof(PlanDev));
+        ctx->h_afix[M] = nullptr;
+        ctx->epoch++;
+    }
     const int W = (M + 63) / 64;                            // 64-bit words per coalition row
     const size_t S_even = ((size_t)S + 1) & ~(size_t)1;     // TMA bulk copies move 16-byte multiples
     CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S_even * W));
@@ -616,8 +636,8 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(double) * S_even, ctx->stream));
     CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
     CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
-    ctx->plan_allocs.push_back(dz); ctx->plan_allocs.push_back(dw); ctx->plan_allocs.push_back(dc);
-    ctx->plan_allocs.push_back(di);
+    ctx->plan_allocs[M].push_back(dz); ctx->plan_allocs[M].push_back(dw); ctx->plan_allocs[M].push_back(dc);
+    ctx->plan_allocs[M].push_back(di);
     CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S * W, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
@@ -628,7 +648,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     } else {
         double* scratch = nullptr;
         CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(double) * (M - 1) * (M - 1)));
-        ctx->plan_allocs.push_back(scratch);
+        ctx->plan_allocs[M].push_back(scratch);
         size_t smem = sizeof(double) * (size_t)(M - 1) * (M - 1);
         CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dks::plan_factor_wide_kernel<<<1, 1024, smem, ctx->stream>>>(dz, dw, S, M, dc, di, scratch, ctx->d_status);
@@ -649,7 +669,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         double* dme = nullptr;
         CUDA_TRY(cudaMalloc((void**)&dm, sizeof(float) * (size_t)ctx->N * pd.S_pad));
         CUDA_TRY(cudaMalloc((void**)&dme, sizeof(double) * (size_t)pd.S_pad));
-        ctx->plan_allocs.push_back(dm); ctx->plan_allocs.push_back(dme);
+        ctx->plan_allocs[M].push_back(dm); ctx->plan_allocs[M].push_back(dme);
         long long total = (long long)ctx->N * pd.S_pad;
         dks::shared_path::plan_dme_kernel<<<cdiv(pd.S_pad, 128), 128, 0, ctx->stream>>>(dz, W, S, pd.S_pad, ctx->d_BW, ctx->d_scores,
                                                                                        ctx->N, ctx->G, ctx->scale, dme);
@@ -665,7 +685,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
             float* pm = nullptr; double* dv = nullptr;
             CUDA_TRY(cudaMalloc((void**)&pm, sizeof(float) * (size_t)(M - 1) * pd.S_pad));
             CUDA_TRY(cudaMalloc((void**)&dv, sizeof(double) * (M - 1)));
-            ctx->plan_allocs.push_back(pm); ctx->plan_allocs.push_back(dv);
+            ctx->plan_allocs[M].push_back(pm); ctx->plan_allocs[M].push_back(dv);
             long long tot = (long long)(M - 1) * pd.S_pad;
             dks::shared_path::plan_pmat_kernel<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(dz, dw, di, S, pd.S_pad, M, pm);
             dks::shared_path::plan_dvec_kernel<<<M - 1, 32, 0, ctx->stream>>>(dz, pm, S, pd.S_pad, M, dv);
@@ -688,8 +708,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
 int dks_clear_plans(dks_ctx* ctx) {
     BIND(ctx);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    for (void* p : ctx->plan_allocs) cudaFree(p);
-    ctx->plan_allocs.clear();
+    free_plan_allocs(ctx, -1);
     ctx->epoch++;
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
     memset(ctx->h_afix, 0, sizeof(ctx->h_afix));
@@ -720,7 +739,7 @@ int dks_set_plan_sampling(dks_ctx* ctx, int M, int nfixed, int n_full, int n_pai
     BIND(ctx);
     double* af = nullptr;
     CUDA_TRY(cudaMalloc((void**)&af, sizeof(double) * (M - 1) * (M - 1)));
-    ctx->plan_allocs.push_back(af);
+    ctx->plan_allocs[M].push_back(af);
     dks::plan_prefix_normal_kernel<<<1, 256, sizeof(double) * (M - 1) * (M - 1), ctx->stream>>>(pd.z, pd.w, nfixed, M, af);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());

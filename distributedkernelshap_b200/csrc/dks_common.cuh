@@ -117,7 +117,7 @@ struct dks_ctx {
     // plans
     PlanDev h_plans[DKS_MAX_GROUPS + 1];
     PlanDev* d_plans = nullptr;
-    std::vector<void*> plan_allocs;
+    std::vector<void*> plan_allocs[DKS_MAX_GROUPS + 1];   // device buffers owned by the plan of each M (freed on replace)
     int max_plan_S = 0;
     // per-instance plans drawn on the device (plan_mode 1)
     int plan_mode = 0;

@@ -48,7 +48,8 @@ class GpuKernelExplainer:
         if plan_mode not in ("shared", "per_instance"):
             raise ValueError("plan_mode must be 'shared' or 'per_instance'")
         if seed is not None:
-            np.random.seed(seed)
+            np.random.seed(seed)           # the reference's constructor side effect (kernel_shap.py:225-228)
+        self.seed = None if seed is None else int(seed)
         self.plan_mode = plan_mode
         self.plan_seed = 0 if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self.lib = _cabi.load()
@@ -156,6 +157,18 @@ class GpuKernelExplainer:
                 "l1_reg=False (as SURVEY.md §7 prescribes for both sides of a comparison)")
         return bool(risky)
 
+    def shared_plan(self, M, nsamples="auto"):
+        """The coalition plan every instance with ``M`` varying groups shares under ``plan_mode='shared'`` (also the
+        source of the enumerated prefix of device-drawn plans).  With a ``seed`` the sampled part comes from a private
+        ``RandomState`` keyed by (seed, M, rows): the same plan on every worker, thread and rank whatever the order in
+        which they meet the M values.  Without a seed it is drawn from the global legacy stream at first use, like the
+        reference's unseeded explainer."""
+        rng = None
+        if self.seed is not None:
+            S, _ = resolve_nsamples(M, nsamples)
+            rng = np.random.RandomState((self.seed * 1000003 + 7919 * M + S) & 0xFFFFFFFF)
+        return build_plan(M, nsamples, rng=rng)
+
     def _ensure_shared_plans(self, hist, nsamples):
         for M in range(2, self.data.groups_size + 1):
             if hist[M] == 0:
@@ -164,7 +177,7 @@ class GpuKernelExplainer:
             _cabi.check(self.lib.dks_has_shared_plan(self._ctx, M, C.byref(present)))
             if present.value:
                 continue
-            plan = build_plan(M, nsamples)  # draws from the global legacy stream, like the reference
+            plan = self.shared_plan(M, nsamples)
             _cabi.check(self.lib.dks_set_shared_plan(self._ctx, M, plan.S, _cabi.ptr(plan.zbits), _cabi.ptr(plan.weights)))
             nfixed, n_full, n_paired, cdf, weight_left = sampling_info(plan)
             if len(cdf) > 32:

@@ -104,8 +104,8 @@ class DistributedExplainer:
 
         if sparse.issparse(X):
             X = X.toarray()
-        slices = batch_slices(X.shape[0], self.batch_size, self.n_jobs)
-        items = [((idx, X[sl]), sl.start) for idx, sl in enumerate(slices)]
+        slices = [sl for sl in batch_slices(X.shape[0], self.batch_size, self.n_jobs) if sl.stop > sl.start]
+        items = [((idx, X[sl]), sl.start) for idx, sl in enumerate(slices)]      # (fewer rows than workers: no empty batches)
 
         def call(actor, item, start):
             return self.target_fn(actor, item, kwargs={**kwargs, "row_offset": start})

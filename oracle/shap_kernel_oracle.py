@@ -271,7 +271,9 @@ class KernelExplainerOracle:
         float64 summation order.
     """
 
-    def __init__(self, model, data, link="identity", faithful_run=False, record_plans=False, rng=None):
+    def __init__(self, model, data, link="identity", faithful_run=False, record_plans=False, rng=None,
+                 chunk_rows=None):
+        self.chunk_rows = chunk_rows    # coalitions per masked-batch chunk (None: the whole S*N x D batch at once)
         self.link = convert_to_link(link)
         self.model = model
         self.data = convert_to_data(data)
@@ -374,7 +376,10 @@ class KernelExplainerOracle:
             if self.record_plans:
                 self.plans.append((self.varyingInds.copy(), Z.copy(), w.copy()))
 
-            self._run(self._masked_batch(x, Z))
+            if self.chunk_rows:
+                self._run_chunked(x, Z, int(self.chunk_rows))
+            else:
+                self._run(self._masked_batch(x, Z))
 
             phi = np.zeros((G, self.D))
             for d in range(self.D):
@@ -414,6 +419,25 @@ class KernelExplainerOracle:
         else:
             ey = np.einsum("sjd,j->sd", y.reshape(S, self.N, self.D), self.data.weights)
         self.y = y
+        self.ey = ey
+
+    def _run_chunked(self, x, Z, chunk):
+        """allocate/addsample/run over `chunk` coalitions at a time: the same rows, model calls and weighted background
+        means as ``_run(_masked_batch(x, Z))`` without holding the whole S*N x D batch (17 GB for BASELINE configs[3])."""
+        S = Z.shape[0]
+        ey = np.zeros((S, self.D))
+        for s0 in range(0, S, chunk):
+            Zc = Z[s0:s0 + chunk]
+            c = Zc.shape[0]
+            synth = np.tile(self.data.data, (c, 1)).reshape(c, self.N, self.P)
+            for j in range(self.M):
+                grp = self.varyingFeatureGroups[j]
+                rows = np.nonzero(Zc[:, j] == 1)[0]
+                if len(rows):
+                    synth[np.ix_(rows, np.arange(self.N), grp)] = x[0, grp]
+            y = np.reshape(np.asarray(self.model(synth.reshape(c * self.N, self.P))), (c, self.N, self.D))
+            ey[s0:s0 + c] = np.einsum("sjd,j->sd", y, self.data.weights)
+        self.y = None
         self.ey = ey
 
     # ---- solve(): constrained weighted least squares ------------------------------------------------

@@ -58,3 +58,12 @@ def rel_err(got, want):
     got, want = np.asarray(got), np.asarray(want)
     scale = np.maximum(np.abs(want).max(axis=-1, keepdims=True), 1e-12)
     return float((np.abs(got - want) / scale).max())
+
+
+def elementwise_excess(got, want, rtol=1e-5, atol=1e-9):
+    """Element-wise criterion |got - want| <= rtol |want| + atol: returns (fraction of elements violating it, the
+    largest |got - want| / (rtol |want| + atol)).  Complements ``rel_err`` (error against the instance's largest
+    |phi|), which lets a small component hide behind a large one."""
+    got, want = np.asarray(got), np.asarray(want)
+    ratio = np.abs(got - want) / (rtol * np.abs(want) + atol)
+    return float((ratio > 1.0).mean()), float(ratio.max())

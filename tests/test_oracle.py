@@ -85,6 +85,33 @@ def test_plan_invariants_adult():
     assert (nss, nps) == (6, 5) and abs(wv.sum() - 1) < 1e-15
 
 
+@pytest.mark.parametrize("M,S,R", [(12, 300, 250), (9, 300, 300)])
+def test_sampled_estimate_is_centred_on_the_exact_shapley_values(M, S, R):
+    """Statistical pin of what the analytic tests cannot reach -- the SAMPLED part of the plan (subset-size
+    distribution, duplicate folding, complement rows, the rescaling of the sampled weights to the mass the enumerated
+    sizes left): over R independent seeds the mean of the sampled KernelSHAP estimate must agree with the exact Shapley
+    values (brute-force subset formula) within the CLT bound.  Wrong rescaling moves the mean by > 8 standard errors,
+    dropping the duplicate counts or the halving of paired sizes by 3-4 in the M = 9 regime where most draws repeat."""
+    prob = make_problem(seed=41, n=1, N=8, widths=(1,) * M)
+    orc = _oracle(prob)
+    x = prob["X"][0]
+
+    def value(mask):
+        rows = prob["bg"].copy()
+        rows[:, mask.astype(bool)] = x[mask.astype(bool)]
+        ey = prob["clf"].predict_proba(rows).mean(0)
+        return orc.link.f(ey) - orc.link.f(orc.fnull)
+    exact = exact_shapley(value, M)[:, 1]
+    est = np.zeros((R, M))
+    for r in range(R):
+        np.random.seed(1000 + r)
+        est[r] = orc.explain(x[None], nsamples=S, l1_reg=False)[:, 1]
+    se = est.std(0, ddof=1) / np.sqrt(R)
+    z = (est.mean(0) - exact) / se
+    assert se.max() < 0.01 * np.abs(exact).max()        # the bound below is a tight one
+    assert np.abs(z).max() < 4.0, z
+
+
 def test_full_plan_is_rng_free():
     a = build_plan(6, 62)[0:2]
     np.random.seed(5)
