@@ -7,6 +7,7 @@
 #include "dks_kernels.cuh"
 #include "dks_tc.cuh"
 #include "dks_shared.cuh"
+#include "dks_fused.cuh"
 #include "dks_sampler.cuh"
 
 namespace {
@@ -92,6 +93,10 @@ int ensure_workspace(dks_ctx* ctx, int n) {
     TRY(dev_alloc(&ctx->d_dlink, (size_t)n * C));
     TRY(dev_alloc(&ctx->d_idx_full, (size_t)n));
     TRY(dev_alloc(&ctx->d_idx_other, (size_t)n));
+    TRY(dev_alloc(&ctx->d_acc, (size_t)n * 24));
+    TRY(dev_alloc(&ctx->d_done, (size_t)n));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_acc, 0, sizeof(long long) * (size_t)n * 24, ctx->stream));   // the fused kernel leaves
+    CUDA_TRY(cudaMemsetAsync(ctx->d_done, 0, sizeof(int) * (size_t)n, ctx->stream));             // both zeroed behind it
     ctx->cap_n = n;
     ctx->epoch++;            // buffers moved: a captured graph holds the old addresses
     return DKS_OK;
@@ -241,7 +246,45 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
                       pg.S == dks_effective_S(G, ctx->nsamples_req);
     if (kernel == DKS_KERNEL_SHARED && !fast && ext_z == nullptr && pg.z != nullptr)
         return fail(DKS_ERR_UNSUPPORTED, "shared-plan fast path needs the binary-logistic head and uniform background weights");
-    if (fast) {
+    // the general kernel below (instances that are not on the shared-plan path) forks off here and joins at the end
+    cudaStream_t gstream = ctx->stream;
+    if (fast && ctx->side_stream != nullptr) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        gstream = ctx->side_stream;
+    }
+    auto join = [&]() -> cudaError_t {
+        if (gstream == ctx->stream) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(ctx->ev_join, gstream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        return e;
+    };
+    dks::shared_path::FusedConfig fcfg;
+    const bool fused = fast && ctx->opt_fused && pg.pmat64 != nullptr && pg.W == 1 &&
+                       dks::shared_path::fused_config(ctx->N, G, pg.S_pad, ctx->sm_count, ctx->max_smem_optin,
+                                                      ctx->opt_fused_ni, ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
+    ctx->last_fused = fused;
+    if (fused) {
+        // link + projection solve inside the coalition kernel: no (sum p1, sum p0) buffer, no separate solve launch
+        dks::shared_path::FusedParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.n = n; fp.N = ctx->N; fp.G = G; fp.C = ctx->C; fp.S = pg.S; fp.S_pad = pg.S_pad; fp.link = ctx->link; fp.B = fcfg.B;
+        fp.scale = ctx->scale; fp.DmT = pg.dmT; fp.dme = pg.dme; fp.z = pg.z; fp.XT = ctx->d_XT; fp.list = ctx->d_idx_full;
+        fp.count = ctx->d_counts; fp.pmat64 = pg.pmat64; fp.dvec = pg.dvec64; fp.dlink = ctx->d_dlink;
+        fp.linkfnull = ctx->d_linkfnull; fp.fnull = ctx->d_fnull; fp.acc = ctx->d_acc; fp.done = ctx->d_done; fp.phi = phi_dev;
+        if (ctx->peer_world > 1 && ctx->push_in_kernel) {
+            for (int r = 0; r < ctx->peer_world; ++r) {
+                double* slab = ctx->peer_base[r] + (long long)ctx->peer_rank * ctx->peer_slab;
+                if (slab == phi_dev) continue;               // phi is written in place into the local slab
+                fp.peer_phi[fp.npeers++] = slab;
+            }
+        }
+        CUDA_TRY(dks::shared_path::launch_explain_fused(fp, fcfg, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        p.list = ctx->d_idx_other;
+        p.count = ctx->d_counts + 1;
+    } else if (fast) {
         const int S = pg.S, S_pad = pg.S_pad;
         size_t need = (size_t)n * S_pad;
         if (need > ctx->cap_sums) { TRY(dev_alloc(&ctx->d_sums, need)); ctx->cap_sums = need; ctx->epoch++; }
@@ -292,9 +335,10 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (!fast)
             return fail(DKS_ERR_UNSUPPORTED, "more than 64 groups needs the shared-plan path (binary-logistic head, uniform "
                         "background weights, kernel 'auto' or 'shared', shared plan of M=%d uploaded)", G);
-        dks::flag_unsupported_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_counts + 1, G, ctx->d_status);
+        dks::flag_unsupported_kernel<<<1, 1, 0, gstream>>>(ctx->d_counts + 1, G, ctx->d_status);
         ctx->launches += 1;
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(join());
         CUDA_TRY(record_ev(ctx, 3));
         return DKS_OK;
     }
@@ -304,7 +348,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (!dks::tc_supported(ctx, p))
             return fail(DKS_ERR_UNSUPPORTED, "tcgen05 kernel does not support this shape/head (N=%d G=%d act=%d)", ctx->N,
                         ctx->G, ctx->act);
-        TRY(dks::tc_launch(ctx, p));
+        TRY(dks::tc_launch(ctx, p, gstream));
     } else {
         const bool sfm = ctx->act == DKS_ACT_SOFTMAX;
         size_t smem = dks::simt_smem_bytes(S_cap, ctx->N, ctx->G, sfm ? ctx->R : 1, sfm ? ctx->C : 1);
@@ -317,10 +361,11 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         if (per_sm > 8) per_sm = 8;
         int grid = ctx->sm_count * per_sm;
         if (grid > n) grid = n;
-        dks::explain_simt_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+        dks::explain_simt_kernel<<<grid, 256, smem, gstream>>>(p);
         ctx->launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(join());
     CUDA_TRY(record_ev(ctx, 3));
     return DKS_OK;
 }
@@ -368,12 +413,23 @@ int dks_create(dks_ctx** out, int device) {
     dks_ctx* ctx = new dks_ctx();
     ctx->device = device;
     { const char* e = getenv("DKS_GRAPH"); ctx->graph_enabled = !(e && e[0] == '0'); }
+    {
+        auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+        ctx->opt_fused = env_int("DKS_FUSED", 1);
+        ctx->opt_fused_ni = env_int("DKS_FUSED_NI", 0);
+        ctx->opt_fused_warps = env_int("DKS_FUSED_WARPS", 0);
+        ctx->opt_fused_B = env_int("DKS_FUSED_B", 0);
+        ctx->push_in_kernel = env_int("DKS_PUSH_IN_KERNEL", 1) != 0;
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc((void**)&ctx->d_plans, sizeof(ctx->h_plans)));
     CUDA_TRY(cudaMemset(ctx->d_plans, 0, sizeof(ctx->h_plans)));
     CUDA_TRY(cudaMalloc((void**)&ctx->d_hist, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4)));   // histogram, status, list counts
@@ -395,7 +451,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
-    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums);
+    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done);
     dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
@@ -403,6 +459,9 @@ int dks_destroy(dks_ctx* ctx) {
     free_plan_allocs(ctx, -1);
     dks::tc_release(ctx);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DKS_OK;
@@ -693,6 +752,20 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
             CUDA_TRY(cudaGetLastError());
             pd.pmat = pm; pd.dvec = dv;
         }
+        // float64 P, row-major per coalition, for the fused kernel (link + solve inside the coalition kernel)
+        if (W == 1 && M - 1 <= 24) {
+            const int kpad = dks::shared_path::fused_kpad(M);
+            double* pm64 = nullptr; double* dv64 = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&pm64, sizeof(double) * (size_t)kpad * pd.S_pad));
+            CUDA_TRY(cudaMalloc((void**)&dv64, sizeof(double) * kpad));
+            ctx->plan_allocs[M].push_back(pm64); ctx->plan_allocs[M].push_back(dv64);
+            long long tot = (long long)kpad * pd.S_pad;
+            dks::shared_path::plan_pmat64_kernel<<<cdiv(tot, 256), 256, 0, ctx->stream>>>(dz, dw, di, S, pd.S_pad, M, kpad, pm64);
+            dks::shared_path::plan_dvec64_kernel<<<kpad, 32, 0, ctx->stream>>>(dz, pm64, S, M, kpad, dv64);
+            ctx->launches += 2;
+            CUDA_TRY(cudaGetLastError());
+            pd.pmat64 = pm64; pd.dvec64 = dv64; pd.kpad = kpad;
+        }
     }
     ctx->h_plans[M] = pd;
     ctx->epoch++;
@@ -846,6 +919,13 @@ static int launch_push(dks_ctx* ctx, const double* phi_dev) {
         pp.dst[pp.npeers++] = slab;
     }
     if (pp.npeers == 0) return DKS_OK;
+    if (ctx->last_fused && ctx->push_in_kernel) {
+        // the fused kernel stored its instances into the peers' buffers as it finished them: only the general kernels' rows are left
+        dks::push_rows_kernel<<<8, 256, 0, ctx->stream>>>(phi_dev, pp, ctx->d_idx_other, ctx->d_counts + 1, ctx->cur_n, ctx->G, ctx->C);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return DKS_OK;
+    }
     dim3 grid(8, pp.npeers);
     dks::push_phi_kernel<<<grid, 256, 0, ctx->stream>>>(phi_dev, pp, ctx->peer_slab);
     ctx->launches += 1;
@@ -977,6 +1057,20 @@ int dks_last_status(dks_ctx* ctx, int* detail) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (detail) *detail = ctx->h_status[1];
     return check_status(ctx);
+}
+
+int dks_set_option(dks_ctx* ctx, const char* name, int value) {
+    REQUIRE(ctx && name, "dks_set_option: bad arguments");
+    const std::string key(name);
+    if (key == "fused") ctx->opt_fused = value;
+    else if (key == "fused_ni") ctx->opt_fused_ni = value;
+    else if (key == "fused_warps") ctx->opt_fused_warps = value;
+    else if (key == "fused_batch") ctx->opt_fused_B = value;
+    else if (key == "push_in_kernel") ctx->push_in_kernel = value != 0;
+    else if (key == "graph") ctx->graph_enabled = value != 0;
+    else return fail(DKS_ERR_INVALID, "dks_set_option: unknown option '%s'", name);
+    ctx->epoch++;                      // a captured graph holds the old launch sequence
+    return DKS_OK;
 }
 
 int dks_set_kernel(dks_ctx* ctx, int kernel) {

@@ -21,6 +21,9 @@ struct PlanDev {
     const double* dme;   // [S_pad] row exponents: Dm rows are normalised so that their largest entry is ~1
     const float* pmat;   // [(M-1)][S_pad] P = inv(E^T W E) E^T W (float32): beta = P y - delta * dvec
     const double* dvec;  // [(M-1)] P z_L
+    const double* pmat64;  // [S_pad][kpad] float64 P, one row per coalition (fused kernel), NULL if not built
+    const double* dvec64;  // [kpad] P z_L with the float64 P
+    int kpad;
     int S;
     int S_pad;
     int W;               // 64-bit words per row
@@ -153,6 +156,8 @@ struct dks_ctx {
     int* d_idx_other = nullptr;  // [n] the rest
     float2* d_sums = nullptr;    // [n][S_pad] (sum p1, sum p0) of the shared fast path
     size_t cap_sums = 0;
+    long long* d_acc = nullptr;  // [n][24] fixed-point partial beta of the fused kernel (zero between launches)
+    int* d_done = nullptr;       // [n] row groups delivered per instance (zero between launches)
     double* d_phi = nullptr;
     size_t cap_phi = 0;
     double* h_phi_pin = nullptr;  // pinned staging for results going to pageable host memory
@@ -186,7 +191,15 @@ struct dks_ctx {
     int peer_world = 0, peer_rank = 0;
     long long peer_slab = 0;                       // doubles per slab
     double* peer_base[16] = {};                    // device pointers to each rank's [world][slab] buffer
+    bool push_in_kernel = true;                    // the solve epilogues store phi into the peers' buffers themselves
+    // tuning knobs (dks_set_option; defaults from the environment at dks_create: DKS_FUSED, DKS_FUSED_NI, ...)
+    int opt_fused = 1, opt_fused_ni = 0, opt_fused_warps = 0, opt_fused_B = 0;
+    bool last_fused = false;                       // the last explain ran the fused shared-plan kernel
 
+    // the general kernel for the instances the shared-plan path does not take runs on a side stream, next to the fused kernel
+    // (it is usually empty: a serialised empty launch cost 6 us per step)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
 };

@@ -500,6 +500,20 @@ __global__ void push_phi_kernel(const double* __restrict__ src, PeerPush pp, lon
     if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n_doubles - 1] = src[n_doubles - 1];
 }
 
+// Same, for the rows of an instance list only (the fused shared-plan kernel has already stored its instances into the
+// peers' buffers; what the general kernels computed still has to travel).  phi is [C][n][G].
+__global__ void push_rows_kernel(const double* __restrict__ src, PeerPush pp, const int* __restrict__ list,
+                                 const int* __restrict__ count, int n, int G, int C) {
+    const int cnt = *count;
+    const long long per = (long long)C * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < cnt * per; idx += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(idx / per), rem = (int)(idx - q * per), c = rem / G, g = rem - c * G;
+        const size_t off = ((size_t)c * n + list[q]) * G + g;
+        const double v = src[off];
+        for (int r = 0; r < pp.npeers; ++r) pp.dst[r][off] = v;
+    }
+}
+
 // an instance list that must be empty (shapes no kernel covers): report instead of computing
 __global__ void flag_unsupported_kernel(const int* __restrict__ count, int detail, int* __restrict__ status) {
     if (*count > 0 && atomicCAS(&status[0], 0, DKS_ERR_UNSUPPORTED) == 0) status[1] = detail;

@@ -881,7 +881,7 @@ inline bool tc_supported(const dks_ctx* ctx, const ExplainParams& p) {
     return true;
 }
 
-inline int tc_launch(dks_ctx* ctx, const ExplainParams& p) {
+inline int tc_launch(dks_ctx* ctx, const ExplainParams& p, cudaStream_t stream) {
     tc::TcParams tp;
     tp.p = p;
     tp.BW = ctx->d_BW;
@@ -901,7 +901,7 @@ inline int tc_launch(dks_ctx* ctx, const ExplainParams& p) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return DKS_ERR_CUDA;
     int grid = ctx->sm_count < p.n ? ctx->sm_count : p.n;
-    kern<<<grid, tc::NTHREADS, smem, ctx->stream>>>(tp);
+    kern<<<grid, tc::NTHREADS, smem, stream>>>(tp);
     ctx->launches += 1;
     return DKS_OK;
 }

@@ -127,6 +127,11 @@ class GpuKernelExplainer:
         _cabi.check(self.lib.dks_set_kernel(self._ctx, code))
         self.kernel = kernel
 
+    def set_option(self, name, value):
+        """Tuning knob of the C library (``dks_set_option``): 'fused', 'fused_ni', 'fused_warps', 'fused_batch',
+        'push_in_kernel', 'graph'."""
+        _cabi.check(self.lib.dks_set_option(self._ctx, str(name).encode(), int(value)))
+
     # ------------------------------------------------------------------------------------------------------
     def _set_nsamples(self, nsamples):
         req = 0 if nsamples in ("auto", None) else int(nsamples)
