@@ -55,6 +55,7 @@ def parse_args():
                     help="shared: one coalition plan per M for all instances (default, the headline); per_instance: a fresh "
                          "plan per instance drawn on the GPU (what shap does on the CPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-oracle timing")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip the secondary leg (the other plan mode)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="instances the CPU baseline explains")
     return ap.parse_args()
 
@@ -74,7 +75,7 @@ def config_dict(world, kernel, plan_mode="shared", collective="none"):
                         "bg=100, nsamples=2048, l1_reg=False, logit link",
             "instances_per_gpu": N_INSTANCES, "global_instances": N_INSTANCES * world, "background": N_BACKGROUND,
             "nsamples": NSAMPLES, "features": 49, "groups": 12,
-            "plan": "shared per M (seed 0)" if plan_mode == "shared" else "per instance, drawn on the GPU (Philox, seed 0)",
+            "plan": PLAN_LABEL[plan_mode],
             "parallelism": f"dp{world} (instances sharded, one all-gather of phi)", "collective": collective, "kernel": kernel,
             "l2_flush_between_steps": True}
 
@@ -148,7 +149,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_worker = 2
+    per_worker = 4
     ctx = mp.get_context("spawn")
     times = []
     with ctx.Pool(cores, initializer=_cpu_init) as pool:
@@ -233,6 +234,59 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
+def measure_mode(wl, X, plan_mode, kernel, steps, warmup, flush, stream):
+    """Device-resident and end-to-end throughput of one plan mode on one GPU (the secondary leg of the default line):
+    same step, same timing rules (CUDA events on the engine's stream, L2 flushed between steps)."""
+    import torch
+    from distributedkernelshap_b200.explainers.kernel_shap import KernelShap
+    n, D = X.shape
+    explainer = KernelShap(wl["predictor"].predict_proba, link="logit", feature_names=wl["group_names"], seed=0,
+                           plan_mode=plan_mode)
+    explainer.fit(wl["data"]["background"]["X"]["preprocessed"], group_names=wl["group_names"], groups=wl["groups"])
+    engine = explainer._explainer
+    engine.set_kernel(kernel)
+    G, C = engine.data.groups_size, engine.D
+    engine.get_explanation(X, nsamples=NSAMPLES, l1_reg=False, silent=True)       # plans built + uploaded
+    engine.set_stream(stream.cuda_stream)
+    X_dev = torch.from_numpy(X).cuda()
+    phi_dev = torch.empty((C, n, G), dtype=torch.float64, device="cuda")
+    for _ in range(warmup):
+        flush.zero_()
+        engine.explain_device(X_dev.data_ptr(), n, phi_dev.data_ptr(), nsamples=NSAMPLES)
+    engine.check_status()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        flush.zero_()
+        starts[k].record(stream)
+        engine.explain_device(X_dev.data_ptr(), n, phi_dev.data_ptr(), nsamples=NSAMPLES)
+        ends[k].record(stream)
+    torch.cuda.synchronize()
+    engine.check_status()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
+    X_pin = torch.empty((n, D), dtype=torch.float64).pin_memory()
+    X_pin.copy_(torch.from_numpy(X))
+    X_host = X_pin.numpy()
+    for _ in range(2):
+        engine.get_explanation(X_host, nsamples=NSAMPLES, l1_reg=False, silent=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        engine.get_explanation(X_host, nsamples=NSAMPLES, l1_reg=False, silent=True)
+    torch.cuda.synchronize()
+    e2e = n * steps / (time.perf_counter() - t0)
+    out = {"plan": PLAN_LABEL[plan_mode], "value": n / (ms / 1e3), "unit": "instances/s", "ms_per_step": ms,
+           "e2e": {"value": e2e, "unit": "instances/s", "h2d_bytes_per_step": n * D * 8, "d2h_bytes_per_step": C * n * G * 8},
+           "kernel_ms": engine.last_timings_ms()["coalitions"]}
+    engine.close()
+    return out
+
+
+PLAN_LABEL = {"shared": "shared per M (one plan for every instance with M varying groups; the engine's fast mode)",
+              "per_instance": "per instance, drawn on the GPU (Philox keyed by seed and global row: what shap does on the CPU)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -372,6 +426,33 @@ def run_ours(args):
     h2d = n * D * 8
     d2h = C * n * G * 8
 
+    # ---------------- sustained: back-to-back steps for ~2 s (a clock record with more than one sample) ----------------
+    sustained = None
+    if world == 1:
+        reps = max(200, int(2000.0 / max(ms_per_step, 1e-3)))
+        sam2 = ClockSampler(local_rank)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sam2.start()
+        ev0.record(stream)
+        for _ in range(reps):
+            step_device()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ck = sam2.stop()
+        engine.check_status()
+        sus_ms = ev0.elapsed_time(ev1) / reps
+        sustained = {"steps": reps, "seconds": ev0.elapsed_time(ev1) / 1e3, "ms_per_step": sus_ms, "value": n / (sus_ms / 1e3),
+                     "l2": "warm (no flush between steps)",
+                     "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"],
+                                "samples": ck["samples"]}}
+
+    # ---------------- the other plan mode (same timing rules), so that the driver's record holds both ----------------
+    other = None
+    if world == 1 and not args.no_other_mode:
+        other_mode = "per_instance" if args.plan_mode == "shared" else "shared"
+        other = measure_mode(wl, X, other_mode, args.kernel, args.steps, args.warmup, flush, stream)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -424,6 +505,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "KernelShap._explainer.get_explanation -> dks_explain_host (pinned host X in, host phi out)"},
             "gpu_launches": int(launches), "roofline": roofline}
+    if sustained is not None:
+        line["sustained"] = sustained
+    if other is not None:
+        line["per_instance" if args.plan_mode == "shared" else "shared_plan"] = other
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
     print(json.dumps(line))

@@ -349,6 +349,46 @@ class GpuKernelExplainer:
         self._set_nsamples(nsamples)
         _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n), C.c_void_p(int(phi_dev_ptr))))
 
+    def explain_block_to_device(self, X, nsamples="auto", l1_reg="auto", row_offset=0, silent=None):
+        """Explain host rows ``X`` and leave the shap values ON THE DEVICE: returns a float64 CUDA tensor ``[C, n, G]``
+        (torch owns the buffers; the engine sees raw pointers).  Used by the SPMD path of ``DistributedExplainer`` so that
+        the all-gather runs on what the solve wrote, without a host round trip.  Zero rows give an empty tensor."""
+        import torch
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        n, G = X.shape[0], self.data.groups_size
+        dev = torch.device("cuda", self.device)
+        phi = torch.empty((self.D, n, G), dtype=torch.float64, device=dev)
+        if n == 0:
+            return phi
+        if X.shape[1] != self.P:
+            raise ValueError(f"X has {X.shape[1]} columns, background has {self.P}")
+        self._set_nsamples(nsamples)
+        need_hist = self._l1_guard(l1_reg, nsamples)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if getattr(self, "_block_stream", None) != stream.cuda_stream:
+                self.set_stream(stream.cuda_stream)
+                self._block_stream = stream.cuda_stream
+            X_dev = torch.from_numpy(X).to(dev, non_blocking=True)
+            if self.plan_mode == "per_instance":
+                _cabi.check(self.lib.dks_set_row_offset(self._ctx, int(row_offset)))
+            if need_hist:
+                _cabi.check(self.lib.dks_prepare_dev(self._ctx, C.c_void_p(X_dev.data_ptr()), n))
+                hist = self.m_histogram()
+                self._l1_guard(l1_reg, nsamples, hist)
+                self._ensure_shared_plans(hist, nsamples)
+            for attempt in range(2):
+                _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(X_dev.data_ptr()), n, C.c_void_p(phi.data_ptr())))
+                detail = C.c_int(0)
+                rc = self.lib.dks_last_status(self._ctx, C.byref(detail))            # synchronises the stream
+                if rc == _cabi.DKS_ERR_PLAN_MISSING and attempt == 0:
+                    self._ensure_shared_plans(self.m_histogram(), nsamples)       # first call / new M: build and rerun
+                    continue
+                _cabi.check(rc)
+                break
+        self._last_rows = 0                     # link_predictions() refers to host-path calls only
+        return phi
+
     def set_peers(self, world, rank, gathered_ptrs, slab_doubles):
         """Multi-GPU push all-gather: ``gathered_ptrs[r]`` = device address (mapped in this process) of rank r's gathered
         ``[world, C, n, G]`` buffer; after every ``explain_device`` this rank's phi is stored into slab ``rank`` of every

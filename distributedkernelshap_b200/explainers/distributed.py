@@ -141,6 +141,15 @@ class DistributedExplainer:
         blocks = batch_slices(n, None, world)          # np.array_split rule
         counts = [b.stop - b.start for b in blocks]
         mine = X[blocks[rank]]
+        engine = self.pool[0]
+        # GPUs + NCCL: the block stays on the device between the solve and the collective (one D2H of the gathered rows)
+        if (self.batch_size is None and "plans" not in kwargs and hasattr(engine, "explain_block_to_device")
+                and parallel._dist().get_backend() == "nccl"):
+            local_dev = engine.explain_block_to_device(mine, row_offset=blocks[rank].start, **kwargs)
+            gathered = parallel.allgather_rows_device(local_dev, counts)
+            if not engine.return_attribute("vector_out"):
+                return gathered[0]
+            return [gathered[c] for c in range(gathered.shape[0])]
         if mine.shape[0] > 0:
             local_slices = batch_slices(mine.shape[0], self.batch_size, 1)
             results = [self.target_fn(self.pool[0], (idx, mine[sl]),

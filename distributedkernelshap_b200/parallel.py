@@ -81,6 +81,33 @@ def allgather_rows(local, counts):
     return np.concatenate([recv[r][:, :counts[r]] for r in range(world)], axis=1)
 
 
+def allgather_rows_device(local_dev, counts):
+    """Same collective for a block that is still on the GPU: ``local_dev`` [C, n_r, G] float64 CUDA tensor.  All-gathers on
+    the device (NCCL), puts the rows in global order on the device, and makes ONE device-to-host copy into pinned memory
+    (torch's caching host allocator: no cudaHostAlloc per call); returns a NumPy view [C, sum(counts), G] that owns it.
+    Replaces the D2H -> H2D -> all-gather -> D2H x world round trip of ``allgather_rows`` on the SPMD host path."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    C, nr, G = local_dev.shape
+    pad = max(counts)
+    if nr == pad:
+        send = local_dev.contiguous()
+    else:
+        send = torch.zeros((C, pad, G), dtype=torch.float64, device=local_dev.device)
+        send[:, :nr] = local_dev
+    recv = torch.empty((world, C, pad, G), dtype=torch.float64, device=local_dev.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
+    if all(c == pad for c in counts):
+        ordered = recv.permute(1, 0, 2, 3).reshape(C, world * pad, G)
+    else:
+        ordered = torch.cat([recv[r][:, :counts[r]] for r in range(world)], dim=1)
+    host = torch.empty(ordered.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(ordered, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 class PeerGather:
     """Gathered ``[world, C, n, G]`` float64 buffer in symmetric (peer-mapped) memory, one per rank.
 

@@ -447,20 +447,21 @@ class KernelExplainerOracle:
 
         nonzero_inds = np.arange(self.M)
         if (self.l1_reg not in ["auto", False, 0]) or (fraction_evaluated < 0.2 and self.l1_reg == "auto"):
-            from sklearn.linear_model import Lasso, LassoLarsIC, lars_path
             w_aug = np.hstack((self.kernelWeights * (self.M - s), self.kernelWeights * s))
             w_sqrt_aug = np.sqrt(w_aug)
             eyAdj_aug = np.hstack((eyAdj, eyAdj - (self.link.f(self.fx[dim]) - self.link.f(self.fnull[dim]))))
             eyAdj_aug *= w_sqrt_aug
             mask_aug = np.transpose(w_sqrt_aug * np.transpose(np.vstack((self.maskMatrix, self.maskMatrix - 1))))
-            if isinstance(self.l1_reg, str) and self.l1_reg.startswith("num_features("):
-                r = int(self.l1_reg[len("num_features("):-1])
-                nonzero_inds = lars_path(mask_aug, eyAdj_aug, max_iter=r)[1]
-            elif self.l1_reg in ("auto", "bic", "aic"):
-                c = "aic" if self.l1_reg == "auto" else self.l1_reg
-                nonzero_inds = np.nonzero(LassoLarsIC(criterion=c).fit(mask_aug, eyAdj_aug).coef_)[0]
+            if isinstance(self.l1_reg, str):
+                # 'num_features(r)' -> lars_path(max_iter=r); 'auto' / 'aic' / 'bic' -> LassoLarsIC: scikit-learn 0.23.2
+                # semantics (the reference's pin), restated in sklearn_lars_restated.py -- the scikit-learn installed
+                # here (1.9) normalises and scores differently and would select other features
+                from .sklearn_lars_restated import select_features
+                nonzero_inds = select_features(self.l1_reg, mask_aug, eyAdj_aug)
             else:
+                from sklearn.linear_model import Lasso          # a float: fixed regularisation strength
                 nonzero_inds = np.nonzero(Lasso(alpha=self.l1_reg).fit(mask_aug, eyAdj_aug).coef_)[0]
+            self.last_nonzero_inds = np.asarray(nonzero_inds)
 
         if len(nonzero_inds) == 0:
             return np.zeros(self.M)
