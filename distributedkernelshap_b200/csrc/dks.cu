@@ -93,9 +93,9 @@ int ensure_workspace(dks_ctx* ctx, int n) {
     TRY(dev_alloc(&ctx->d_dlink, (size_t)n * C));
     TRY(dev_alloc(&ctx->d_idx_full, (size_t)n));
     TRY(dev_alloc(&ctx->d_idx_other, (size_t)n));
-    TRY(dev_alloc(&ctx->d_acc, (size_t)n * 24));
+    TRY(dev_alloc(&ctx->d_acc, (size_t)n * 16));
     TRY(dev_alloc(&ctx->d_done, (size_t)n));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_acc, 0, sizeof(long long) * (size_t)n * 24, ctx->stream));   // the fused kernel leaves
+    CUDA_TRY(cudaMemsetAsync(ctx->d_acc, 0, sizeof(long long) * (size_t)n * 16, ctx->stream));   // the fused kernel leaves
     CUDA_TRY(cudaMemsetAsync(ctx->d_done, 0, sizeof(int) * (size_t)n, ctx->stream));             // both zeroed behind it
     ctx->cap_n = n;
     ctx->epoch++;            // buffers moved: a captured graph holds the old addresses
@@ -262,7 +262,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     dks::shared_path::FusedConfig fcfg;
     const bool fused = fast && ctx->opt_fused && pg.pmat64 != nullptr && pg.W == 1 &&
                        dks::shared_path::fused_config(ctx->N, G, pg.S_pad, ctx->sm_count, ctx->max_smem_optin,
-                                                      ctx->opt_fused_ni, ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
+                                                      ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
     ctx->last_fused = fused;
     if (fused) {
         // link + projection solve inside the coalition kernel: no (sum p1, sum p0) buffer, no separate solve launch
@@ -753,7 +753,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
             pd.pmat = pm; pd.dvec = dv;
         }
         // float64 P, row-major per coalition, for the fused kernel (link + solve inside the coalition kernel)
-        if (W == 1 && M - 1 <= 24) {
+        if (W == 1 && M <= 16) {
             const int kpad = dks::shared_path::fused_kpad(M);
             double* pm64 = nullptr; double* dv64 = nullptr;
             CUDA_TRY(cudaMalloc((void**)&pm64, sizeof(double) * (size_t)kpad * pd.S_pad));

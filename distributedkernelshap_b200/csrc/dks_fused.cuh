@@ -69,7 +69,9 @@ inline size_t fused_smem_bytes(int warps, int kpad, int B) {
            DKS_LOGTAB_SIZE * sizeof(LogTabEntry);
 }
 
-template <int NI, int KPAD, int NWARPS>
+// NCT: background rows at compile time (0 = run-time p.N): with NCT the chunk loop unrolls completely (static tensor-memory
+// offsets, no loop control, the tail folded).  B (instances parked per warp) is a power of two.
+template <int NCT, int KPAD, int NWARPS>
 __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(FusedParams p, int warps_used, int cstride) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ uint32_t s_tmem;
@@ -99,48 +101,54 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
     const uint32_t tbase = s_tmem;
 
     if (active) {
+        constexpr int MAXCH = MAXN / 16;
         const int s = rg * 32 + lane;
         const int cnt = *p.count;
-        const int N = p.N, G = p.G, nA = G - 1;
+        const int N = NCT ? NCT : p.N, G = p.G, nA = G - 1;
         const int nfull = N / 16, ntail = N - nfull * 16;
         const int nq_t = ntail >> 2, rem_t = ntail & 3;
         const int nch = nfull + (ntail > 0 ? 1 : 0);
         const uint32_t taddr = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * cstride);
         const double es = p.dme[s];
         // ---- this warp's 32 rows of Dm into tensor memory: pair sums and pair products per quad of columns (0,2) (1,3)
-        for (int c = 0; c * 16 < N; ++c) {
-            float v[16];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const int j = c * 16 + jj;
-                v[jj] = j < N ? p.DmT[(size_t)j * p.S_pad + s] : 0.f;
-            }
-            const int nv = c < nfull ? 16 : ntail;
+        for (int c = 0; c < MAXCH; ++c) {
+            if (c < nch) {
+                float v[16];
 #pragma unroll
-            for (int jj = 0; jj < 16; jj += 4) {
-                if (jj + 3 < nv) {
-                    const float d0 = v[jj], d1 = v[jj + 1], d2 = v[jj + 2], d3 = v[jj + 3];
-                    v[jj] = d0 + d2; v[jj + 1] = d1 + d3; v[jj + 2] = d0 * d2; v[jj + 3] = d1 * d3;
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int j = c * 16 + jj;
+                    v[jj] = j < N ? p.DmT[(size_t)j * p.S_pad + s] : 0.f;
                 }
-            }
-            if (c < nfull) {
-                tmem_st16(taddr + c * 16, v);
-            } else {
-                // four columns at a time: the slice stride is N rounded up to 4 (a wider store would run into the next slice)
-                if (ntail > 0) tmem_st4(taddr + c * 16 + 0, v[0], v[1], v[2], v[3]);
-                if (ntail > 4) tmem_st4(taddr + c * 16 + 4, v[4], v[5], v[6], v[7]);
-                if (ntail > 8) tmem_st4(taddr + c * 16 + 8, v[8], v[9], v[10], v[11]);
-                if (ntail > 12) tmem_st4(taddr + c * 16 + 12, v[12], v[13], v[14], v[15]);
+                const int nv = c < nfull ? 16 : ntail;
+#pragma unroll
+                for (int jj = 0; jj < 16; jj += 4) {
+                    if (jj + 3 < nv) {
+                        const float d0 = v[jj], d1 = v[jj + 1], d2 = v[jj + 2], d3 = v[jj + 3];
+                        v[jj] = d0 + d2; v[jj + 1] = d1 + d3; v[jj + 2] = d0 * d2; v[jj + 3] = d1 * d3;
+                    }
+                }
+                if (c < nfull) {
+                    tmem_st16(taddr + c * 16, v);
+                } else {
+                    // four columns at a time: the slice stride is N rounded up to 4 (a wider store would run into the next slice)
+                    if (ntail > 0) tmem_st4(taddr + c * 16 + 0, v[0], v[1], v[2], v[3]);
+                    if (ntail > 4) tmem_st4(taddr + c * 16 + 4, v[4], v[5], v[6], v[7]);
+                    if (ntail > 8) tmem_st4(taddr + c * 16 + 8, v[8], v[9], v[10], v[11]);
+                    if (ntail > 12) tmem_st4(taddr + c * 16 + 12, v[12], v[13], v[14], v[15]);
+                }
             }
         }
         tmem_st_wait();
 
         const uint64_t zz = s < p.S ? p.z[s] : 0ull;
-        const int ntab = (G + 3) / 4;
+        const int ntab = (G + 3) / 4;                     // <= 4 (the host sends wider problems down the unfused path)
         const f32x2 one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
         const double lf1 = p.linkfnull[1], f1 = p.fnull[1], inv_n = 1.0 / (double)N;
         const size_t slab = (size_t)p.n * G;
         const int my_n = part < cnt ? (cnt - part + nparts - 1) / nparts : 0;     // instances this warp streams
+        const bool row_ok = s < p.S;
+        const int bmask = B - 1;
 
         // ---- the turn-around: lane = instance of the batch, loop over the warp's 32 rows
         auto flush = [&](int bstart, int bcount) {
@@ -194,131 +202,78 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
             }
         };
 
-        // table entries of a(i, s): loaded one iteration ahead when there are at most four nibble tables
-        const bool ahead = ntab <= 4;
-        int off[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) off[t] = t * 16 + (int)((zz >> (4 * t)) & 15ull);
-        int i_cur[NI], i_nx[NI];
-        double nx[NI][4];
-#pragma unroll
-        for (int u = 0; u < NI; ++u) {
-            i_cur[u] = u < my_n ? p.list[part + u * nparts] : 0;
-            i_nx[u] = NI + u < my_n ? p.list[part + (NI + u) * nparts] : 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) nx[u][t] = 0.0;
-            if (ahead && u < my_n) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (t < ntab) nx[u][t] = __ldg(p.XT + (size_t)i_cur[u] * ntab * 16 + off[t]);
-            }
+        // a(i, s) = sum over the row's nibbles of one table entry each; the entries of the NEXT instance are loaded one
+        // iteration ahead (the offsets depend on the row only), the instance index two ahead.  No branches: tables the
+        // problem does not have point at entry [0][0] (the empty subset: exactly 0.0), and past the last instance the
+        // loads repeat the last one.
+        const size_t xstride = (size_t)ntab * 16;
+        const double* xb0 = p.XT + (int)(zz & 15ull);
+        const double* xb1 = p.XT + (ntab > 1 ? 16 + (int)((zz >> 4) & 15ull) : 0);
+        const double* xb2 = p.XT + (ntab > 2 ? 32 + (int)((zz >> 8) & 15ull) : 0);
+        const double* xb3 = p.XT + (ntab > 3 ? 48 + (int)((zz >> 12) & 15ull) : 0);
+        const int last_it = my_n > 0 ? my_n - 1 : 0;
+        int i_nx = my_n > 0 ? p.list[part + (1 < my_n ? 1 : 0) * nparts] : 0;
+        double nx0 = 0.0, nx1 = 0.0, nx2 = 0.0, nx3 = 0.0;
+        if (my_n > 0) {
+            const size_t o = (size_t)p.list[part] * xstride;
+            nx0 = __ldg(xb0 + o); nx1 = __ldg(xb1 + o); nx2 = __ldg(xb2 + o); nx3 = __ldg(xb3 + o);
         }
 
-        for (int it0 = 0; it0 < my_n; it0 += NI) {
-            float A[NI];
-            bool valid[NI];
-            bool risky_l = false;
-#pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                valid[u] = it0 + u < my_n;
-                double a;
-                if (ahead) {
-                    a = (nx[u][0] + nx[u][1]) + (nx[u][2] + nx[u][3]);
-                    i_cur[u] = i_nx[u];
-                    if (it0 + NI + u < my_n) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (t < ntab) nx[u][t] = __ldg(p.XT + (size_t)i_cur[u] * ntab * 16 + off[t]);
-                    }
-                    if (it0 + 2 * NI + u < my_n) i_nx[u] = p.list[part + (it0 + 2 * NI + u) * nparts];
-                } else {
-                    a = 0.0;
-                    if (valid[u]) {
-                        const double* xt = p.XT + (size_t)p.list[part + (it0 + u) * nparts] * ntab * 16;
-                        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
-                        for (int t = 0; t < 16 && t < ntab; t += 2) {
-                            a0 += __ldg(xt + t * 16 + (int)((zz >> (4 * t)) & 15ull));
-                            if (t + 1 < ntab) a1 += __ldg(xt + (t + 1) * 16 + (int)((zz >> (4 * t + 4)) & 15ull));
-                        }
-                        a = a0 + a1;
-                    }
-                }
-                a += es;
-                a = fmin(fmax(a, -120.0), 120.0);
-                const double an = rint(a);
-                A[u] = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
-                risky_l = risky_l || (valid[u] && A[u] > 1.0e18f);
+        for (int it = 0; it < my_n; ++it) {
+            const double a = ((nx0 + nx1) + (nx2 + nx3)) + es;
+            {
+                const size_t o = (size_t)i_nx * xstride;
+                nx0 = __ldg(xb0 + o); nx1 = __ldg(xb1 + o); nx2 = __ldg(xb2 + o); nx3 = __ldg(xb3 + o);
+                const int it2 = it + 2 < last_it ? it + 2 : last_it;
+                i_nx = p.list[part + it2 * nparts];
             }
-            float s1[NI], s0[NI];
-            const bool risky = __any_sync(0xffffffffu, risky_l);
-            if (risky) {
+            // A = 2^a = 2^n 2^f, n = rint(a) through the 1.5 * 2^52 trick (no conversion instructions), |f| <= 1/2; the
+            // exponent is clamped to [-120, 120] (saturated scores; the clamped scalar path below takes A > 1e18)
+            const double tm = a + 6755399441055744.0;
+            int an_i = __double2loint(tm);
+            an_i = an_i < -120 ? -120 : (an_i > 120 ? 120 : an_i);
+            const float A = ex2_approx((float)(a - (tm - 6755399441055744.0))) * __int_as_float((127 + an_i) << 23);
+            float s1, s0;
+            if (__any_sync(0xffffffffu, A > 1.0e18f)) {
                 // A^2 would leave the fp32 range: clamped scalar path on the raw row from global memory (saturated scores)
-#pragma unroll
-                for (int u = 0; u < NI; ++u) {
-                    float r1 = 0.f, r0 = 0.f;
-                    for (int j = 0; j + 1 < N; j += 2)
-                        pair_acc<true>(A[u], p.DmT[(size_t)j * p.S_pad + s], p.DmT[(size_t)(j + 1) * p.S_pad + s], r1, r0);
-                    if (N & 1) single_acc(A[u], p.DmT[(size_t)(N - 1) * p.S_pad + s], r1, r0);
-                    s1[u] = r1; s0[u] = r0;
-                }
+                float r1 = 0.f, r0 = 0.f;
+                for (int j = 0; j + 1 < N; j += 2)
+                    pair_acc<true>(A, p.DmT[(size_t)j * p.S_pad + s], p.DmT[(size_t)(j + 1) * p.S_pad + s], r1, r0);
+                if (N & 1) single_acc(A, p.DmT[(size_t)(N - 1) * p.S_pad + s], r1, r0);
+                s1 = r1; s0 = r0;
             } else {
-                f32x2 A2[NI], AA2[NI], AA2x2[NI];
-                f32x2 acc1[NI][2], acc0[NI][2];
-                float t1s[NI], t0s[NI];
+                const float AA = A * A;
+                const f32x2 A2 = f2_pack(A, A), AA2 = f2_pack(AA, AA), AA2x2 = f2_pack(2.f * AA, 2.f * AA);
+                f32x2 acc1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, acc0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+                float t1s = 0.f, t0s = 0.f;
+                float v[2][16];
+                tc::tmem_ld16(taddr, v[0]);
 #pragma unroll
-                for (int u = 0; u < NI; ++u) {
-                    const float AA = A[u] * A[u];
-                    A2[u] = f2_pack(A[u], A[u]); AA2[u] = f2_pack(AA, AA); AA2x2[u] = f2_pack(2.f * AA, 2.f * AA);
-                    acc1[u][0] = acc1[u][1] = acc0[u][0] = acc0[u][1] = f2_pack(0.f, 0.f);
-                    t1s[u] = t0s[u] = 0.f;
-                }
-                float va[16], vb[16];
-                tc::tmem_ld16(taddr, va);
-                for (int c = 0; c < nch; c += 2) {
-                    tc::tmem_ld_wait(va);
-                    if (c + 1 < nch) tc::tmem_ld16(taddr + (c + 1) * 16, vb);
-#pragma unroll
-                    for (int u = 0; u < NI; ++u) {
-                        if (c < nfull) chunk_sums<16>(va, A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
-                        else chunk_sums_rt(va, nq_t, rem_t, A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
-                    }
-                    if (c + 1 < nch) {
-                        tc::tmem_ld_wait(vb);
-                        if (c + 2 < nch) tc::tmem_ld16(taddr + (c + 2) * 16, va);
-#pragma unroll
-                        for (int u = 0; u < NI; ++u) {
-                            if (c + 1 < nfull) chunk_sums<16>(vb, A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
-                            else chunk_sums_rt(vb, nq_t, rem_t, A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
-                        }
+                for (int c = 0; c < MAXCH; ++c) {
+                    if (c < nch) {
+                        tc::tmem_ld_wait(v[c & 1]);
+                        if (c + 1 < nch) tc::tmem_ld16(taddr + (c + 1) * 16, v[(c + 1) & 1]);
+                        if (c < nfull) chunk_sums<16>(v[c & 1], A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
+                        else chunk_sums_rt(v[c & 1], nq_t, rem_t, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < NI; ++u) {
-                    float q0, q1, q2, q3;
-                    f2_unpack(f2_add(acc1[u][0], acc1[u][1]), q0, q1);
-                    f2_unpack(f2_add(acc0[u][0], acc0[u][1]), q2, q3);
-                    s1[u] = (q0 + q1) + t1s[u];
-                    s0[u] = (q2 + q3) + t0s[u];
-                }
+                float q0, q1, q2, q3;
+                f2_unpack(f2_add(acc1[0], acc1[1]), q0, q1);
+                f2_unpack(f2_add(acc0[0], acc0[1]), q2, q3);
+                s1 = (q0 + q1) + t1s;
+                s0 = (q2 + q3) + t0s;
             }
             // ---- link in place, row parked for the turn-around
-#pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                if (valid[u]) {
-                    double y = 0.0;
-                    if (s < p.S) {
-                        if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(s1[u], s0[u], s_logtab) - lf1;
-                        else y = (double)s1[u] * inv_n - f1;
-                    }
-                    sYw[lane * ystride + ((it0 + u) % B)] = y;
-                }
+            double y = 0.0;
+            if (row_ok) {
+                if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(s1, s0, s_logtab) - lf1;
+                else y = (double)s1 * inv_n - f1;
             }
-            const int done_cnt = it0 + NI < my_n ? it0 + NI : my_n;
-            if ((done_cnt % B) == 0 || done_cnt == my_n) {
-                const int bstart = (done_cnt - 1) / B * B;
+            const int slot = it & bmask;
+            sYw[lane * ystride + slot] = y;
+            if (slot == bmask || it == my_n - 1) {
                 __syncwarp();
-                flush(bstart, done_cnt - bstart);
+                flush(it - slot, slot + 1);
                 __syncwarp();
             }
         }
@@ -361,28 +316,26 @@ __global__ void plan_dvec64_kernel(const uint64_t* __restrict__ z, const double*
     if (threadIdx.x == 0) dvec[k] = acc;
 }
 
-inline int fused_kpad(int G) { return G - 1 <= 12 ? 12 : 24; }
+inline int fused_kpad(int G) { return G - 1 <= 12 ? 12 : 16; }
 
 struct FusedConfig { int ni, warps, B, slices; size_t smem; };
 
-// picks (instances per pass, warps per CTA, batch) for a shape; returns false when the fused kernel does not apply.
-// want_ni / want_warps / want_B: 0 = default (tuning knobs, dks_set_option)
-inline bool fused_config(int N, int G, int S_pad, int sm_count, int max_smem, int want_ni, int want_warps, int want_B,
-                         FusedConfig* cfg) {
-    if (G < 2 || G - 1 > 24 || N > MAXN) return false;
+// picks (warps per CTA, batch) for a shape; returns false when the fused kernel does not apply.
+// want_warps / want_B: 0 = default (tuning knobs, dks_set_option)
+inline bool fused_config(int N, int G, int S_pad, int sm_count, int max_smem, int want_warps, int want_B, FusedConfig* cfg) {
+    if (G < 2 || G > 16 || N > MAXN) return false;                        // at most four nibble tables, 15 coefficients
     const int cstride = (N + 3) / 4 * 4, reach = (N + 15) / 16 * 16;
     int slices = 5;
     while (slices > 1 && (slices - 1) * cstride + reach > 512) --slices;
     int warps = 4 * slices;
     if (want_warps == 16 && warps > 16) warps = 16;
     const int kpad = fused_kpad(G);
-    int B = want_B > 0 ? want_B : 32;
-    if (B > 32) B = 32;
-    while (B > 4 && fused_smem_bytes(warps, kpad, B) + 1024 > (size_t)max_smem) B >>= 1;
-    if (B & 1) B += 1;                                                    // two instances per pass fill slots in pairs
+    int B = 32;
+    if (want_B == 16 || want_B == 8) B = want_B;
+    while (B > 8 && fused_smem_bytes(warps, kpad, B) + 1024 > (size_t)max_smem) B >>= 1;
     if (fused_smem_bytes(warps, kpad, B) + 1024 > (size_t)max_smem) return false;
     if ((long long)sm_count * warps < S_pad / 32) return false;          // every row group needs a warp
-    cfg->ni = want_ni == 2 ? 2 : 1;
+    cfg->ni = 1;
     cfg->warps = warps; cfg->B = B; cfg->slices = warps / 4;
     cfg->smem = fused_smem_bytes(warps, kpad, B);
     return true;
@@ -392,20 +345,26 @@ inline cudaError_t launch_explain_fused(const FusedParams& p, const FusedConfig&
     const int kpad = fused_kpad(p.G);
     const int cstride = (p.N + 3) / 4 * 4;
     cudaError_t err = cudaSuccess;
-#define DKS_FUSED_LAUNCH(NI, KP, NW)                                                                                  \
+#define DKS_FUSED_LAUNCH(NCT, KP, NW)                                                                                 \
     do {                                                                                                              \
-        err = cudaFuncSetAttribute(explain_shared_fused_kernel<NI, KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        err = cudaFuncSetAttribute(explain_shared_fused_kernel<NCT, KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)cfg.smem);                                                                    \
         if (err == cudaSuccess)                                                                                       \
-            explain_shared_fused_kernel<NI, KP, NW><<<grid, 32 * NW, cfg.smem, stream>>>(p, cfg.warps, cstride);     \
+            explain_shared_fused_kernel<NCT, KP, NW><<<grid, 32 * NW, cfg.smem, stream>>>(p, cfg.warps, cstride);    \
     } while (0)
+    // background sizes with a compile-time specialisation (the chunk loop unrolls completely); everything else takes the
+    // run-time version
     const int nw = cfg.warps > 16 ? 20 : 16;
-    if (cfg.ni == 2) {
-        if (kpad == 12) { if (nw == 20) DKS_FUSED_LAUNCH(2, 12, 20); else DKS_FUSED_LAUNCH(2, 12, 16); }
-        else { if (nw == 20) DKS_FUSED_LAUNCH(2, 24, 20); else DKS_FUSED_LAUNCH(2, 24, 16); }
+    if (kpad == 12) {
+        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 12, 20);
+        else if (p.N == 128 && nw == 16) DKS_FUSED_LAUNCH(128, 12, 16);
+        else if (p.N == 64 && nw == 20) DKS_FUSED_LAUNCH(64, 12, 20);
+        else if (nw == 20) DKS_FUSED_LAUNCH(0, 12, 20);
+        else DKS_FUSED_LAUNCH(0, 12, 16);
     } else {
-        if (kpad == 12) { if (nw == 20) DKS_FUSED_LAUNCH(1, 12, 20); else DKS_FUSED_LAUNCH(1, 12, 16); }
-        else { if (nw == 20) DKS_FUSED_LAUNCH(1, 24, 20); else DKS_FUSED_LAUNCH(1, 24, 16); }
+        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 16, 20);
+        else if (nw == 20) DKS_FUSED_LAUNCH(0, 16, 20);
+        else DKS_FUSED_LAUNCH(0, 16, 16);
     }
 #undef DKS_FUSED_LAUNCH
     return err;

@@ -98,6 +98,7 @@ class GpuKernelExplainer:
         self.fnull = fnull
         self.expected_value = expected if self.vector_out else float(expected[0])
         self._nsamples_req = None
+        self._plan_cache = {}
         self._link_fx_parts = []
         self._last_rows = 0
         self._check_model_against_callable(bg)
@@ -168,11 +169,16 @@ class GpuKernelExplainer:
         ``RandomState`` keyed by (seed, M, rows): the same plan on every worker, thread and rank whatever the order in
         which they meet the M values.  Without a seed it is drawn from the global legacy stream at first use, like the
         reference's unseeded explainer."""
+        S, _ = resolve_nsamples(M, nsamples)
+        cached = self._plan_cache.get((M, S))
+        if cached is not None:
+            return cached
         rng = None
         if self.seed is not None:
-            S, _ = resolve_nsamples(M, nsamples)
             rng = np.random.RandomState((self.seed * 1000003 + 7919 * M + S) & 0xFFFFFFFF)
-        return build_plan(M, nsamples, rng=rng)
+        plan = build_plan(M, nsamples, rng=rng)
+        self._plan_cache[(M, S)] = plan         # what was uploaded is what this accessor reports
+        return plan
 
     def _ensure_shared_plans(self, hist, nsamples):
         for M in range(2, self.data.groups_size + 1):

@@ -369,11 +369,12 @@ class KernelShap(Explainer, FitMixin):
 
         self.background_data = self._get_data(background_data, group_names, groups, weights, **kwargs)
         explainer_args = (self.predictor, self.background_data)
-        explainer_kwargs = {'link': self.link}
+        # the seed travels with every replica (reference: only in a distributed context, kernel_shap.py:779; the engine keys
+        # its private plan streams by it, so one GPU, a pool of GPUs and torchrun ranks all evaluate the same plans)
+        explainer_kwargs = {'link': self.link, 'seed': self.seed}
         if self.plan_mode != 'shared':
-            explainer_kwargs.update(plan_mode=self.plan_mode, seed=self.seed)
+            explainer_kwargs.update(plan_mode=self.plan_mode)
         if self.distribute:
-            explainer_kwargs['seed'] = self.seed  # every worker seeds its own stream
             self._explainer = DistributedExplainer(
                 self.distributed_opts,
                 KernelExplainerWrapper,
