@@ -54,6 +54,8 @@ SIGNATURES = {
     "dks_set_shared_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dks_clear_plans": (C.c_int, [C.c_void_p]),
     "dks_has_shared_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "dks_set_l1": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "dks_set_l1_tables": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_double, C.c_double, C.c_int]),
     "dks_set_plan_sampling": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double]),
     "dks_set_plan_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
     "dks_set_row_offset": (C.c_int, [C.c_void_p, C.c_int64]),

@@ -8,6 +8,7 @@
 #include "dks_tc.cuh"
 #include "dks_shared.cuh"
 #include "dks_fused.cuh"
+#include "dks_l1.cuh"
 #include "dks_sampler.cuh"
 
 namespace {
@@ -260,7 +261,15 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         return e;
     };
     dks::shared_path::FusedConfig fcfg;
-    const bool fused = fast && ctx->opt_fused && pg.pmat64 != nullptr && pg.W == 1 &&
+    const bool l1 = ctx->l1_mode != 0;
+    if (l1) {
+        if (ext_z != nullptr || ctx->plan_mode == 1)
+            return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection runs on shared plans only");
+        if (!fast || ctx->h_l1[G].gram_raw == nullptr || ctx->h_l1[G].S != pg.S)
+            return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection needs the shared-plan path (binary-logistic head, uniform "
+                        "background weights) and the l1 tables of the M=%d plan (dks_set_l1_tables)", G);
+    }
+    const bool fused = fast && !l1 && ctx->opt_fused && pg.pmat64 != nullptr && pg.W == 1 &&
                        dks::shared_path::fused_config(ctx->N, G, pg.S_pad, ctx->sm_count, ctx->max_smem_optin,
                                                       ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
     ctx->last_fused = fused;
@@ -297,7 +306,43 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         wp.uniform_w = 1; wp.sums = ctx->d_sums; wp.z = pg.z; wp.w = pg.w; wp.ainv = pg.ainv; wp.dlink = ctx->d_dlink;
         wp.linkfnull = ctx->d_linkfnull; wp.fnull = ctx->d_fnull; wp.list = ctx->d_idx_full; wp.count = ctx->d_counts;
         wp.phi = phi_dev;
-        if (pg.pmat != nullptr) {
+        if (l1) {
+            // upstream's l1 branch: moments of y per instance, then the LARS path + criterion + restricted WLS, one warp each
+            const dks_ctx::L1Dev& lt = ctx->h_l1[G];
+            const size_t need_m = (size_t)n * (2 * G + 4);
+            if (need_m > ctx->cap_mom) { TRY(dev_alloc(&ctx->d_mom, need_m)); ctx->cap_mom = need_m; ctx->epoch++; }
+            dks::l1::Params lp;
+            memset(&lp, 0, sizeof(lp));
+            lp.n = n; lp.N = ctx->N; lp.G = G; lp.C = ctx->C; lp.S = S; lp.S_pad = S_pad; lp.link = ctx->link;
+            lp.mode = ctx->l1_mode; lp.kfeat = ctx->l1_k; lp.sums = ctx->d_sums; lp.z = pg.z; lp.w = pg.w;
+            lp.t.gram_raw = lt.gram_raw; lp.t.gram_norm = lt.gram_norm; lp.t.colsum = lt.colsum; lp.t.scale = lt.scale;
+            lp.t.bz = lt.bz; lp.t.gram_w = lt.gram_w; lp.t.b = lt.b; lp.t.sqab = lt.sqab; lp.t.sum_b = lt.sum_b;
+            lp.t.sum_sqb = lt.sum_sqb; lp.t.n_aug = lt.n_aug;
+            lp.dlink = ctx->d_dlink; lp.linkfnull = ctx->d_linkfnull; lp.fnull = ctx->d_fnull; lp.list = ctx->d_idx_full;
+            lp.count = ctx->d_counts; lp.mom = ctx->d_mom; lp.phi = phi_dev; lp.status = ctx->d_status;
+            const size_t msm = sizeof(double) * (size_t)S;
+            if (msm + 8192 > (size_t)ctx->max_smem_optin)
+                return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection: %d coalitions per plan exceed the shared-memory staging", S);
+            const int mgrid = n < ctx->sm_count * 2 ? n : ctx->sm_count * 2;
+            if (pg.W == 1) {
+                CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_moments_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+                dks::l1::l1_moments_kernel<1><<<mgrid, dks::l1::MOM_THREADS, msm, ctx->stream>>>(lp);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_moments_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+                dks::l1::l1_moments_kernel<2><<<mgrid, dks::l1::MOM_THREADS, msm, ctx->stream>>>(lp);
+            }
+            const size_t per_warp = dks::l1::lars_smem_per_warp(G);
+            int wpc = (int)(((size_t)ctx->max_smem_optin - 2048) / per_warp);
+            if (wpc < 1) return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection: the %d x %d Cholesky factor does not fit shared memory", G, G);
+            if (wpc > 8) wpc = 8;
+            int per_sm = (int)((size_t)ctx->max_smem_optin / (per_warp * wpc + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;
+            int lgrid = (n + wpc - 1) / wpc;
+            if (lgrid > ctx->sm_count * per_sm) lgrid = ctx->sm_count * per_sm;
+            CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_lars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpc)));
+            dks::l1::l1_lars_kernel<<<lgrid, 32 * wpc, per_warp * wpc, ctx->stream>>>(lp, wpc);
+        } else if (pg.pmat != nullptr) {
             dks::shared_path::WlsPmatParams pp;
             pp.n = n; pp.N = ctx->N; pp.G = G; pp.C = ctx->C; pp.S = S; pp.S_pad = S_pad; pp.link = ctx->link; pp.uniform_w = 1;
             pp.sums = ctx->d_sums; pp.pmat = pg.pmat; pp.dvec = pg.dvec; pp.dlink = ctx->d_dlink;
@@ -325,6 +370,15 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         CUDA_TRY(cudaGetLastError());
         p.list = ctx->d_idx_other;      // the general kernel below takes the remaining instances
         p.count = ctx->d_counts + 1;
+    }
+    if (l1 && !ctx->l1_others_plain) {
+        // instances with a partial varying set would need their own selection: reported, not computed
+        dks::flag_unsupported_kernel<<<1, 1, 0, gstream>>>(ctx->d_counts + 1, G, ctx->d_status);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(join());
+        CUDA_TRY(record_ev(ctx, 3));
+        return DKS_OK;
     }
     if (G > 64) {
         // two-word coalition rows exist on the shared-plan path only: anything left over is reported, not computed
@@ -451,7 +505,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
-    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done);
+    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom);
     dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
@@ -617,6 +671,7 @@ int dks_fit(dks_ctx* ctx) {
     if (any_plan_allocs(ctx)) {   // plans carry tables derived from the background/model: drop them
         free_plan_allocs(ctx, -1);
         memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+        memset(ctx->h_l1, 0, sizeof(ctx->h_l1));
         ctx->max_plan_S = 0;
         CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
     }
@@ -684,6 +739,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         free_plan_allocs(ctx, M);
         memset(&ctx->h_plans[M], 0, sizeof(PlanDev));
+        memset(&ctx->h_l1[M], 0, sizeof(ctx->h_l1[M]));
         ctx->h_afix[M] = nullptr;
         ctx->epoch++;
     }
@@ -784,6 +840,7 @@ int dks_clear_plans(dks_ctx* ctx) {
     free_plan_allocs(ctx, -1);
     ctx->epoch++;
     memset(ctx->h_plans, 0, sizeof(ctx->h_plans));
+    memset(ctx->h_l1, 0, sizeof(ctx->h_l1));
     memset(ctx->h_afix, 0, sizeof(ctx->h_afix));
     memset(ctx->h_sinfo, 0, sizeof(ctx->h_sinfo));
     ctx->max_plan_S = 0;
@@ -794,6 +851,46 @@ int dks_clear_plans(dks_ctx* ctx) {
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present) {
     REQUIRE(ctx && present && M >= 0 && M <= DKS_MAX_GROUPS, "dks_has_shared_plan: bad arguments");
     *present = (ctx->h_plans[M].z != nullptr && ctx->h_plans[M].S == dks_effective_S(M, ctx->nsamples_req)) ? 1 : 0;
+    return DKS_OK;
+}
+
+int dks_set_l1(dks_ctx* ctx, int mode, int k, int others_plain) {
+    REQUIRE(ctx && mode >= 0 && mode <= 3, "dks_set_l1: mode must be 0 (off), 1 (aic), 2 (bic) or 3 (num_features)");
+    REQUIRE(mode != 3 || k >= 1, "dks_set_l1: num_features needs k >= 1");
+    if (mode != ctx->l1_mode || k != ctx->l1_k || others_plain != ctx->l1_others_plain) ctx->epoch++;
+    ctx->l1_mode = mode; ctx->l1_k = k; ctx->l1_others_plain = others_plain;
+    return DKS_OK;
+}
+
+int dks_set_l1_tables(dks_ctx* ctx, int M, const double* gram_raw, const double* gram_norm, const double* colsum,
+                      const double* scale, const double* bz, const double* gram_w, const double* b_rows,
+                      const double* sqab_rows, double sum_b, double sum_sqb, int n_aug) {
+    BIND(ctx);
+    REQUIRE(M >= 2 && M <= DKS_MAX_GROUPS, "dks_set_l1_tables: M out of range");
+    REQUIRE(gram_raw && gram_norm && colsum && scale && bz && gram_w && b_rows && sqab_rows, "dks_set_l1_tables: NULL table");
+    const PlanDev& pd = ctx->h_plans[M];
+    REQUIRE(pd.z != nullptr && n_aug == 2 * pd.S, "dks_set_l1_tables: set the shared plan of M=%d first (n_aug = 2 S)", M);
+    const size_t mm = (size_t)M * M, S = (size_t)pd.S;
+    const size_t total = 3 * mm + 3 * (size_t)M + 2 * S;
+    double* base = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&base, sizeof(double) * total));
+    ctx->plan_allocs[M].push_back(base);
+    dks_ctx::L1Dev d;
+    memset(&d, 0, sizeof(d));
+    double* q = base;
+    auto put = [&](const double* src, size_t cnt, const double** dst) -> cudaError_t {
+        *dst = q;
+        cudaError_t e = cudaMemcpyAsync(q, src, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream);
+        q += cnt;
+        return e;
+    };
+    CUDA_TRY(put(gram_raw, mm, &d.gram_raw)); CUDA_TRY(put(gram_norm, mm, &d.gram_norm)); CUDA_TRY(put(gram_w, mm, &d.gram_w));
+    CUDA_TRY(put(colsum, M, &d.colsum)); CUDA_TRY(put(scale, M, &d.scale)); CUDA_TRY(put(bz, M, &d.bz));
+    CUDA_TRY(put(b_rows, S, &d.b)); CUDA_TRY(put(sqab_rows, S, &d.sqab));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    d.sum_b = sum_b; d.sum_sqb = sum_sqb; d.n_aug = n_aug; d.S = pd.S;
+    ctx->h_l1[M] = d;
+    ctx->epoch++;
     return DKS_OK;
 }
 

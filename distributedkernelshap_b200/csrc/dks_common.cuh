@@ -122,6 +122,16 @@ struct dks_ctx {
     PlanDev* d_plans = nullptr;
     std::vector<void*> plan_allocs[DKS_MAX_GROUPS + 1];   // device buffers owned by the plan of each M (freed on replace)
     int max_plan_S = 0;
+    // l1 feature selection (dks_set_l1 / dks_set_l1_tables): per-M tables on the device
+    struct L1Dev {
+        const double *gram_raw, *gram_norm, *colsum, *scale, *bz, *gram_w, *b, *sqab;
+        double sum_b, sum_sqb;
+        int n_aug, S;
+    };
+    L1Dev h_l1[DKS_MAX_GROUPS + 1] = {};
+    int l1_mode = 0, l1_k = 0, l1_others_plain = 0;
+    double* d_mom = nullptr;     // [n][2G + 4] per-instance moments of y
+    size_t cap_mom = 0;
     // per-instance plans drawn on the device (plan_mode 1)
     int plan_mode = 0;
     uint64_t sampler_seed = 0;

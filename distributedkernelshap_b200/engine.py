@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _cabi
 from .data import DenseData, convert_to_data, convert_to_link
-from .plan import build_plan, pack_dense_plan, resolve_nsamples, sampling_info
+from .plan import build_plan, l1_tables, pack_dense_plan, resolve_nsamples, sampling_info
 from .predictors import extract_linear_spec
 
 logger = logging.getLogger(__name__)
@@ -99,6 +99,8 @@ class GpuKernelExplainer:
         self.expected_value = expected if self.vector_out else float(expected[0])
         self._nsamples_req = None
         self._plan_cache = {}
+        self._l1_uploaded = {}
+        self._l1_state = (0, 0, 0)
         self._link_fx_parts = []
         self._last_rows = 0
         self._check_model_against_callable(bg)
@@ -141,27 +143,65 @@ class GpuKernelExplainer:
             self._nsamples_req = req
 
     def _l1_guard(self, l1_reg, nsamples, hist=None):
-        """The engine solves the plain constrained WLS.  Upstream's ``solve`` first runs an l1 feature selection when
-        ``l1_reg`` asks for it, or under 'auto' when fewer than 20% of the coalition space is evaluated.  Never differ
-        silently: refuse those cases."""
+        """Upstream's ``solve`` runs an l1 feature selection before the constrained WLS when ``l1_reg`` is 'aic' / 'bic' /
+        'num_features(k)', or under 'auto' when fewer than 20% of the coalition space is evaluated.  Without ``hist``:
+        whether the M histogram is needed to decide.  With it: ``(mode, k, others_plain)`` for ``dks_set_l1`` -- the
+        selection runs on the shared-plan path (csrc/dks_l1.cuh) for the instances whose groups all vary; what that path
+        does not cover is refused, never silently solved without the selection."""
         if l1_reg in (False, 0):
-            return False
-        if l1_reg != "auto":
-            raise NotImplementedError(f"l1_reg={l1_reg!r}: l1 feature selection is not implemented in the CUDA engine; "
-                                      "pass l1_reg=False")
-        risky = []
-        for M in range(2, self.data.groups_size + 1):
-            if hist is not None and hist[M] == 0:
-                continue
+            return False if hist is None else (0, 0, 0)
+        G = self.data.groups_size
+        explicit = None
+        if l1_reg in ("aic", "bic"):
+            explicit = (1 if l1_reg == "aic" else 2, 0)
+        elif isinstance(l1_reg, str) and l1_reg.startswith("num_features("):
+            explicit = (3, int(l1_reg[len("num_features("):-1]))
+        elif l1_reg != "auto":
+            raise NotImplementedError(f"l1_reg={l1_reg!r}: a fixed Lasso strength is not implemented in the CUDA engine; "
+                                      "use 'auto', 'aic', 'bic', 'num_features(k)' or False")
+
+        def needs(M):
+            if explicit is not None:
+                return True
             S, max_s = resolve_nsamples(M, nsamples)
-            if S / max_s < 0.2:
-                risky.append(M)
-        if risky and hist is not None:
+            return S / max_s < 0.2
+        if hist is None:
+            return explicit is not None or any(needs(M) for M in range(2, G + 1))
+        present = [M for M in range(2, G + 1) if hist[M] > 0]
+        wanting = [M for M in present if needs(M)]
+        if not wanting:
+            return (0, 0, 0)
+        partial = [M for M in wanting if M != G]
+        if partial:
             raise NotImplementedError(
-                f"l1_reg='auto' would run LassoLarsIC feature selection for instances with M in {risky} varying groups "
-                "(under 20% of the coalition space sampled); the CUDA engine implements the plain WLS only -- pass "
-                "l1_reg=False (as SURVEY.md §7 prescribes for both sides of a comparison)")
-        return bool(risky)
+                f"l1_reg={l1_reg!r} selects features for instances with M in {partial} varying groups (a partial varying "
+                "set); the CUDA engine runs the selection for instances whose groups all vary only -- pass l1_reg=False")
+        if self.plan_mode != "shared":
+            raise NotImplementedError("l1 feature selection runs with plan_mode='shared' only")
+        if self.spec.act_code != _cabi.ACT_BINARY_LOGISTIC or not np.allclose(self.data.weights, self.data.weights[0]):
+            raise NotImplementedError("l1 feature selection needs the binary-logistic head and uniform background weights "
+                                      "(the shared-plan path)")
+        mode, k = explicit if explicit is not None else (1, 0)
+        return (mode, k, 1 if len(present) > 1 else 0)
+
+    def _apply_l1(self, l1_reg, nsamples, hist):
+        """Uploads the l1 tables of the G-group plan when the call needs them and tells the library the mode."""
+        mode, k, others_plain = (0, 0, 0) if l1_reg in (False, 0) else self._l1_guard(l1_reg, nsamples, hist)
+        if mode:
+            G = self.data.groups_size
+            S, _ = resolve_nsamples(G, nsamples)
+            if self._l1_uploaded.get(G) != S:
+                self._ensure_shared_plans(hist, nsamples)
+                t = l1_tables(self.shared_plan(G, nsamples))
+                sqab = np.ascontiguousarray(t["sqa"] + t["sqb"])
+                _cabi.check(self.lib.dks_set_l1_tables(
+                    self._ctx, G, _cabi.ptr(t["gram_raw"]), _cabi.ptr(t["gram_norm"]), _cabi.ptr(t["colsum"]),
+                    _cabi.ptr(t["scale"]), _cabi.ptr(t["bz"]), _cabi.ptr(t["gram_w"]), _cabi.ptr(t["b"]), _cabi.ptr(sqab),
+                    t["sum_b"], t["sum_sqb"], t["n_aug"]))
+                self._l1_uploaded[G] = S
+        if (mode, k, others_plain) != self._l1_state:
+            _cabi.check(self.lib.dks_set_l1(self._ctx, mode, k, others_plain))
+            self._l1_state = (mode, k, others_plain)
 
     def shared_plan(self, M, nsamples="auto"):
         """The coalition plan every instance with ``M`` varying groups shares under ``plan_mode='shared'`` (also the
@@ -277,15 +317,20 @@ class GpuKernelExplainer:
             zb, w, stride = self._pack_external_plans(plans, n, nsamples)
             if need_hist:
                 _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), n))
-                self._l1_guard(l1_reg, nsamples, self.m_histogram())
+                if self._l1_guard(l1_reg, nsamples, self.m_histogram())[0]:
+                    raise NotImplementedError("l1 feature selection runs on the engine's shared plans, not on "
+                                              "caller-supplied per-instance plans -- pass l1_reg=False")
+            self._apply_l1(False, nsamples, None)
             _cabi.check(self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), _cabi.ptr(zb), _cabi.ptr(w),
                                                   stride))
         else:
             if need_hist:
                 _cabi.check(self.lib.dks_prepare_host(self._ctx, _cabi.ptr(X), n))
                 hist = self.m_histogram()
-                self._l1_guard(l1_reg, nsamples, hist)
                 self._ensure_shared_plans(hist, nsamples)
+                self._apply_l1(l1_reg, nsamples, hist)
+            else:
+                self._apply_l1(False, nsamples, None)
             rc = self.lib.dks_explain_host(self._ctx, _cabi.ptr(X), n, _cabi.ptr(phi), None, None, 0)
             if rc == _cabi.DKS_ERR_PLAN_MISSING:
                 # first call (or a new M): build the missing plans from the M histogram and run again
@@ -353,6 +398,7 @@ class GpuKernelExplainer:
         buffer ``phi_dev_ptr`` (float64 [C, n, G]) using the shared plans already on the device.  Call ``check_status()``
         after synchronising to learn about missing plans / numerical failures."""
         self._set_nsamples(nsamples)
+        self._apply_l1(False, nsamples, None)             # the device-resident call is the plain constrained WLS
         _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(int(X_dev_ptr)), int(n), C.c_void_p(int(phi_dev_ptr))))
 
     def explain_block_to_device(self, X, nsamples="auto", l1_reg="auto", row_offset=0, silent=None):
@@ -381,8 +427,10 @@ class GpuKernelExplainer:
             if need_hist:
                 _cabi.check(self.lib.dks_prepare_dev(self._ctx, C.c_void_p(X_dev.data_ptr()), n))
                 hist = self.m_histogram()
-                self._l1_guard(l1_reg, nsamples, hist)
                 self._ensure_shared_plans(hist, nsamples)
+                self._apply_l1(l1_reg, nsamples, hist)
+            else:
+                self._apply_l1(False, nsamples, None)
             for attempt in range(2):
                 _cabi.check(self.lib.dks_run_dev(self._ctx, C.c_void_p(X_dev.data_ptr()), n, C.c_void_p(phi.data_ptr())))
                 detail = C.c_int(0)

@@ -271,3 +271,36 @@ def pack_dense_plan(Z):
     k2 = np.arange(M - 64, dtype=np.uint64)
     hi = (Z[:, 64:].astype(np.uint64) << k2[None, :]).sum(axis=1, dtype=np.uint64)
     return np.stack([lo, hi], axis=1)
+
+
+def l1_tables(plan):
+    """Per-plan tables of the l1 feature-selection step (``l1_reg='auto' | 'aic' | 'bic' | 'num_features(k)'`` of upstream
+    ``solve``, which regresses on the AUGMENTED system ``[sqrt(w (M - |z|)) z ; sqrt(w |z|) (z - 1)]``).  Everything that
+    depends on the plan only -- the Gram matrix of the augmented columns, raw and centred / normalised the way
+    scikit-learn 0.23.2's ``LassoLarsIC`` does it, the column sums, the weighted Gram of the plain rows for the final
+    restricted WLS, and the per-row weights -- is formed here once in float64 (host Python, like the plan itself); the
+    engine then needs only per-instance moment vectors of y (``dks_set_l1_tables`` / csrc/dks_l1.cuh).
+
+    Returns a dict of C-contiguous float64 arrays: ``gram_raw`` [M, M], ``gram_norm`` [M, M], ``colsum`` [M],
+    ``scale`` [M], ``bz`` [M] (sum_s b_s z_sk), ``gram_w`` [M, M] (sum_s w_s z_sk z_sl), ``wz`` [M] (sum_s w_s z_sk),
+    ``a`` / ``b`` / ``sqa`` / ``sqb`` [S], and the scalars ``sum_b``, ``sum_sqb``, ``sum_w``, ``n_aug``."""
+    Z = plan.dense().astype(np.float64)
+    w = np.asarray(plan.weights, dtype=np.float64)
+    M = plan.M
+    sz = Z.sum(axis=1)
+    a = w * (M - sz)
+    b = w * sz
+    sqa, sqb = np.sqrt(a), np.sqrt(b)
+    Zc = 1.0 - Z
+    gram_raw = Z.T @ (a[:, None] * Z) + Zc.T @ (b[:, None] * Zc)
+    colsum = Z.T @ sqa - Zc.T @ sqb
+    n_aug = 2 * len(w)
+    gram_c = gram_raw - np.outer(colsum, colsum) / n_aug
+    scale = np.sqrt(np.maximum(np.diag(gram_c), 0.0))
+    scale[scale == 0.0] = 1.0
+    gram_norm = gram_c / np.outer(scale, scale)
+    out = dict(gram_raw=gram_raw, gram_norm=gram_norm, colsum=colsum, scale=scale, bz=Z.T @ b,
+               gram_w=Z.T @ (w[:, None] * Z), wz=Z.T @ w, a=a, b=b, sqa=sqa, sqb=sqb)
+    out = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in out.items()}
+    out.update(sum_b=float(b.sum()), sum_sqb=float(sqb.sum()), sum_w=float(w.sum()), n_aug=int(n_aug))
+    return out

@@ -98,6 +98,19 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
 int dks_clear_plans(dks_ctx* ctx);
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present);
 
+/* ---- l1 feature selection: the l1_reg branch of KernelExplainer.solve (kwargs path kernel_shap.py:836-845, :880) --------
+ * mode 0 = off (plain constrained WLS), 1 = LassoLarsIC 'aic' (what l1_reg='auto' means when under 20% of the coalition
+ * space is sampled), 2 = 'bic', 3 = 'num_features(k)' (lars_path with max_iter = k); scikit-learn 0.23.2 semantics (the
+ * reference's pin).  Runs on the shared-plan path for instances whose groups all vary; others_plain != 0 lets the remaining
+ * instances take the plain WLS (the caller has checked that upstream would not select features for them), 0 reports them
+ * as DKS_ERR_UNSUPPORTED.  dks_set_l1_tables uploads what plan.py:l1_tables computes for the shared plan of M groups (after
+ * dks_set_shared_plan): Gram matrices of the augmented system [M x M], column sums / norms / b-weighted column sums [M], the
+ * w-weighted Gram of the plain rows [M x M], per-row b_s and sqrt(a_s) + sqrt(b_s) [S], and three scalars. */
+int dks_set_l1(dks_ctx* ctx, int mode, int k, int others_plain);
+int dks_set_l1_tables(dks_ctx* ctx, int M, const double* gram_raw, const double* gram_norm, const double* colsum,
+                      const double* scale, const double* bz, const double* gram_w, const double* b_rows,
+                      const double* sqab_rows, double sum_b, double sum_sqb, int n_aug);
+
 /* ---- per-instance plans drawn on the device -----------------------------------------------------------
  * shap.KernelExplainer.explain draws a fresh plan for every instance (the sampling loop that follows the subset
  * enumeration; reached from kernel_shap.py:250/253).  Mode 1 does that on the GPU: the enumerated prefix comes from the

@@ -169,13 +169,16 @@ def test_adult_shape_shared_plan_parity_and_sharding_invariance(kernel):
     np.testing.assert_array_equal(np.concatenate([a[1], b[1]]), got[1])
 
 
-def test_l1_reg_is_refused_not_ignored():
+def test_l1_reg_settings_the_engine_does_not_cover_are_refused_not_ignored():
+    """The l1 selection itself runs on the device (tests/test_gpu_l1.py); what it does not cover raises."""
     prob = make_problem(seed=8, n=4, N=6, widths=(1,) * 16)
     eng = _engine(prob)
     with pytest.raises(NotImplementedError):
-        eng.shap_values(prob["X"], nsamples=200)          # l1_reg='auto' would trigger: 200 / (2^16 - 2) < 0.2
+        eng.shap_values(prob["X"], nsamples=200, l1_reg=0.01)           # fixed Lasso strength
+    per = _engine(prob, plan_mode="per_instance", seed=1)
     with pytest.raises(NotImplementedError):
-        eng.shap_values(prob["X"], nsamples=200, l1_reg="num_features(3)")
+        per.shap_values(prob["X"], nsamples=200)                          # 'auto' would select: shared plans only
+    per.shap_values(prob["X"], nsamples=200, l1_reg=False)
     eng.shap_values(prob["X"], nsamples=200, l1_reg=False)
 
 
@@ -332,8 +335,8 @@ def test_config2_shape_64_features_bg512():
     eng = GpuKernelExplainer(d["predictor"].predict_proba, d["background"], link="logit")
     got = eng.shap_values(d["X_explain"], nsamples=4096, l1_reg=False, plans=[(Z, w) for (_, Z, w) in orc.plans])
     _compare(got, want)
-    with pytest.raises(NotImplementedError):          # reference default l1_reg='auto' would select features here
-        eng.shap_values(d["X_explain"], nsamples=4096)
+    with pytest.raises(NotImplementedError):          # l1 selection runs on the engine's shared plans, not on these
+        eng.shap_values(d["X_explain"], nsamples=4096, plans=[(Z, w) for (_, Z, w) in orc.plans])
 
 
 def test_config2_shape_shared_plan():
