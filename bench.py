@@ -334,15 +334,17 @@ def run_ours(args):
     gather, collective = None, "none"
     if world > 1:
         collective = "nccl all_gather_into_tensor"
-        # measured on this pool (profiles/r1_bench_*gpu_{push,nccl}.log, ms/step push vs NCCL): N=2 0.224 / 0.221,
-        # N=4 0.229 / 0.308, N=8 0.344 / 0.240 (NCCL's in-switch path wins there): push up to 4 ranks, NCCL beyond.
-        # DKS_BENCH_NCCL=1 / DKS_BENCH_PUSH=1 force one or the other.
-        use_push = (world <= 4 or os.environ.get("DKS_BENCH_PUSH", "0") == "1") and os.environ.get("DKS_BENCH_NCCL", "0") != "1"
+        # the solve epilogue stores every finished instance's phi into all peers' gathered buffers over NVLink peer memory
+        # and the explain call ends with the engine's own flag exchange (signal + wait per peer); DKS_BENCH_NCCL=1 forces
+        # ncclAllGather instead, DKS_BENCH_SYMM_BARRIER=1 the symmetric-memory barrier instead of the flags.
+        use_push = os.environ.get("DKS_BENCH_NCCL", "0") != "1"
         if use_push:
             try:
-                gather = parallel.PeerGather(engine, C, n, G, torch.device("cuda", local_rank))
+                own_sync = os.environ.get("DKS_BENCH_SYMM_BARRIER", "0") != "1"
+                gather = parallel.PeerGather(engine, C, n, G, torch.device("cuda", local_rank), own_sync=own_sync)
                 phi_dev = gather.local
-                collective = "push over peer memory (own kernel) + symmetric-memory barrier"
+                collective = ("phi stored into every peer's gathered buffer by the solve epilogue (NVLink peer memory) + " +
+                              ("the engine's flag exchange" if own_sync else "symmetric-memory barrier"))
             except Exception as exc:                      # pragma: no cover - depends on the box
                 print(f"[bench] peer-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
                 gather = None

@@ -65,11 +65,13 @@ SIGNATURES = {
     "dks_get_m_histogram": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dks_run_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dks_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "dks_set_peer_flags": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dks_graph_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dks_get_link_fx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dks_get_varying": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dks_explain_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dks_explain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "dks_summarise_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dks_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "dks_set_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "dks_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -505,7 +505,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
-    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom);
+    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom); dev_free(&ctx->d_step);
     dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
@@ -1030,6 +1030,20 @@ static int launch_push(dks_ctx* ctx, const double* phi_dev) {
     return DKS_OK;
 }
 
+// after the pushes: signal every peer and wait for theirs (no-op without dks_set_peer_flags)
+static int launch_peer_sync(dks_ctx* ctx) {
+    if (ctx->peer_world <= 1 || !ctx->peer_flags_set) return DKS_OK;
+    dks::PeerFlags f;
+    memset(&f, 0, sizeof(f));
+    f.world = ctx->peer_world; f.rank = ctx->peer_rank; f.step = ctx->d_step;
+    f.mine = ctx->peer_flags[ctx->peer_rank];
+    for (int r = 0; r < ctx->peer_world; ++r) f.peer[r] = ctx->peer_flags[r];
+    dks::peer_sync_kernel<<<1, 32, 0, ctx->stream>>>(f, ctx->d_status);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return DKS_OK;
+}
+
 static void drop_graph(dks_ctx* ctx) {
     if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
 }
@@ -1065,6 +1079,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
     int rc = launch_prepare(ctx, X_dev, n);
     if (rc == DKS_OK) rc = launch_explain(ctx, phi_dev, nullptr, nullptr, 0);
     if (rc == DKS_OK) rc = launch_push(ctx, phi_dev);
+    if (rc == DKS_OK) rc = launch_peer_sync(ctx);
     if (capture) {
         ctx->capturing = false;
         cudaGraph_t graph = nullptr;
@@ -1088,6 +1103,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
             TRY(launch_prepare(ctx, X_dev, n));
             TRY(launch_explain(ctx, phi_dev, nullptr, nullptr, 0));
             TRY(launch_push(ctx, phi_dev));
+            TRY(launch_peer_sync(ctx));
         }
     } else if (rc != DKS_OK) {
         return rc;
@@ -1098,7 +1114,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
 int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_ptrs_host, int64_t slab_doubles) {
     REQUIRE(ctx, "dks_set_peers: ctx is NULL");
     ctx->epoch++;
-    if (world <= 1 || gathered_ptrs_host == nullptr) { ctx->peer_world = 0; return DKS_OK; }
+    if (world <= 1 || gathered_ptrs_host == nullptr) { ctx->peer_world = 0; ctx->peer_flags_set = false; return DKS_OK; }
     REQUIRE(world <= 16 && rank >= 0 && rank < world && slab_doubles > 0, "dks_set_peers: bad arguments (at most 16 ranks)");
     for (int r = 0; r < world; ++r) {
         REQUIRE(gathered_ptrs_host[r] != 0 && (gathered_ptrs_host[r] & 15) == 0, "dks_set_peers: peer buffers must be 16-byte aligned");
@@ -1106,6 +1122,23 @@ int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_pt
     }
     REQUIRE((slab_doubles & 1) == 0, "dks_set_peers: slab size must be even (128-bit stores)");
     ctx->peer_world = world; ctx->peer_rank = rank; ctx->peer_slab = slab_doubles;
+    return DKS_OK;
+}
+
+int dks_set_peer_flags(dks_ctx* ctx, const uint64_t* flag_ptrs_host) {
+    BIND(ctx);
+    ctx->epoch++;
+    if (flag_ptrs_host == nullptr) { ctx->peer_flags_set = false; return DKS_OK; }
+    REQUIRE(ctx->peer_world > 1, "dks_set_peer_flags: call dks_set_peers first");
+    for (int r = 0; r < ctx->peer_world; ++r) {
+        REQUIRE(flag_ptrs_host[r] != 0 && (flag_ptrs_host[r] & 7) == 0, "dks_set_peer_flags: flag arrays must be 8-byte aligned");
+        ctx->peer_flags[r] = reinterpret_cast<unsigned long long*>(flag_ptrs_host[r]);
+    }
+    if (!ctx->d_step) {
+        TRY(dev_alloc(&ctx->d_step, (size_t)1));
+        CUDA_TRY(cudaMemset(ctx->d_step, 0, sizeof(unsigned long long)));
+    }
+    ctx->peer_flags_set = true;
     return DKS_OK;
 }
 
@@ -1133,6 +1166,7 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
         dz = ctx->d_extz; dw = ctx->d_extw;
     }
     TRY(launch_explain(ctx, ctx->d_phi, dz, dw, ext_stride));
+    ctx->phi_rows = n;                      // dks_summarise_host works off this buffer
     // results travel through a pinned staging buffer: one asynchronous DMA + one host memcpy instead of the driver's
     // chunked pageable path (the caller's array is ordinary NumPy memory)
     if (need_phi > ctx->cap_phi_pin) {
@@ -1146,6 +1180,49 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     memcpy(phi_host, ctx->h_phi_pin, sizeof(double) * need_phi);
     return check_status(ctx);
+}
+
+int dks_summarise_host(dks_ctx* ctx, int n, const int32_t* seg_offsets_host, int Gp, double* phi_sum_host,
+                       double* mean_abs_host, int32_t* order_host, int32_t* argmax_host) {
+    BIND(ctx);
+    REQUIRE(ctx->prepared && ctx->d_phi != nullptr && n == ctx->cur_n && n == ctx->phi_rows,
+            "dks_summarise_host: the last dks_explain_host call covered %d rows, the caller expects %d", ctx->phi_rows, n);
+    const int G = ctx->G, C = ctx->C;
+    REQUIRE(Gp >= 1 && Gp <= G, "dks_summarise_host: Gp out of range");
+    if (seg_offsets_host) {
+        REQUIRE(seg_offsets_host[0] == 0 && seg_offsets_host[Gp] == G, "dks_summarise_host: segments must cover the %d groups", G);
+        for (int g = 0; g < Gp; ++g) REQUIRE(seg_offsets_host[g + 1] > seg_offsets_host[g], "dks_summarise_host: empty segment");
+    } else {
+        REQUIRE(Gp == G, "dks_summarise_host: without segments Gp must equal the number of groups");
+    }
+    int* d_seg = nullptr; double* d_sum = nullptr; unsigned long long* d_abs = nullptr; double* d_mean = nullptr; int* d_ord = nullptr;
+    int* d_arg = nullptr;
+    const size_t cells = (size_t)C * Gp;
+    TRY(dev_alloc(&d_abs, cells)); TRY(dev_alloc(&d_mean, (size_t)(C + 1) * Gp)); TRY(dev_alloc(&d_ord, (size_t)(C + 1) * Gp));
+    TRY(dev_alloc(&d_arg, (size_t)n));
+    if (seg_offsets_host) {
+        TRY(dev_alloc(&d_seg, (size_t)Gp + 1));
+        CUDA_TRY(cudaMemcpyAsync(d_seg, seg_offsets_host, sizeof(int) * (Gp + 1), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (phi_sum_host) TRY(dev_alloc(&d_sum, cells * n));
+    CUDA_TRY(cudaMemsetAsync(d_abs, 0, sizeof(unsigned long long) * cells, ctx->stream));
+    const long long total = (long long)cells * n;
+    int grid = cdiv(total, 256);
+    if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+    dks::phi_summary_kernel<<<grid, 256, sizeof(unsigned long long) * cells, ctx->stream>>>(
+        ctx->d_phi, C, n, G, d_seg, Gp, d_sum, d_abs, ctx->d_dlink, ctx->d_linkfnull, d_arg);
+    dks::phi_rank_kernel<<<1, 128, 0, ctx->stream>>>(d_abs, C, n, Gp, d_mean, d_ord);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    if (phi_sum_host) CUDA_TRY(cudaMemcpyAsync(phi_sum_host, d_sum, sizeof(double) * cells * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mean_abs_host) CUDA_TRY(cudaMemcpyAsync(mean_abs_host, d_mean, sizeof(double) * (C + 1) * Gp, cudaMemcpyDeviceToHost, ctx->stream));
+    if (order_host) CUDA_TRY(cudaMemcpyAsync(order_host, d_ord, sizeof(int) * (C + 1) * Gp, cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_host) CUDA_TRY(cudaMemcpyAsync(argmax_host, d_arg, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_abs); cudaFree(d_mean); cudaFree(d_ord); cudaFree(d_arg);
+    if (d_seg) cudaFree(d_seg);
+    if (d_sum) cudaFree(d_sum);
+    return DKS_OK;
 }
 
 int dks_last_status(dks_ctx* ctx, int* detail) {

@@ -170,6 +170,7 @@ struct dks_ctx {
     int* d_done = nullptr;       // [n] row groups delivered per instance (zero between launches)
     double* d_phi = nullptr;
     size_t cap_phi = 0;
+    int phi_rows = 0;             // rows of the last dks_explain_host result held in d_phi
     double* h_phi_pin = nullptr;  // pinned staging for results going to pageable host memory
     size_t cap_phi_pin = 0;
     uint64_t* d_extz = nullptr;
@@ -201,6 +202,9 @@ struct dks_ctx {
     int peer_world = 0, peer_rank = 0;
     long long peer_slab = 0;                       // doubles per slab
     double* peer_base[16] = {};                    // device pointers to each rank's [world][slab] buffer
+    unsigned long long* peer_flags[16] = {};       // rank r's flag array [world] (peer-mapped); [peer_rank] is this rank's own
+    bool peer_flags_set = false;
+    unsigned long long* d_step = nullptr;          // device-side step counter of the flag exchange
     bool push_in_kernel = true;                    // the solve epilogues store phi into the peers' buffers themselves
     // tuning knobs (dks_set_option; defaults from the environment at dks_create: DKS_FUSED, DKS_FUSED_NI, ...)
     int opt_fused = 1, opt_fused_ni = 0, opt_fused_warps = 0, opt_fused_B = 0;

@@ -514,6 +514,93 @@ __global__ void push_rows_kernel(const double* __restrict__ src, PeerPush pp, co
     }
 }
 
+// ---- KernelShap.build_explanation post-processing off the resident phi (kernel_shap.py:36-109, :112-207, :952-956) ----------
+// Segment sums over consecutive groups (sum_categories), |.| accumulated per (output, segment) in 2^-40 fixed point
+// (shared-memory atomics per block, one global atomic per block and cell: order-independent), argmax of the raw prediction.
+__global__ void phi_summary_kernel(const double* __restrict__ phi, int C, int n, int G, const int* __restrict__ seg, int Gp,
+                                   double* __restrict__ phi_sum, unsigned long long* __restrict__ absacc,
+                                   const double* __restrict__ dlink, const double* __restrict__ linkfnull,
+                                   int* __restrict__ argmax) {
+    extern __shared__ unsigned long long s_abs[];           // [C * Gp]
+    for (int idx = threadIdx.x; idx < C * Gp; idx += blockDim.x) s_abs[idx] = 0ull;
+    __syncthreads();
+    const long long total = (long long)C * n * Gp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int gp = (int)(idx % Gp);
+        const long long ci = idx / Gp;
+        const int i = (int)(ci % n), c = (int)(ci / n);
+        const int g0 = seg ? seg[gp] : gp, g1 = seg ? seg[gp + 1] : gp + 1;
+        double v = 0.0;
+        for (int g = g0; g < g1; ++g) v += phi[((size_t)c * n + i) * G + g];
+        if (phi_sum) phi_sum[idx] = v;
+        atomicAdd(&s_abs[c * Gp + gp], (unsigned long long)to_fix(fabs(v)));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C * Gp; idx += blockDim.x)
+        if (s_abs[idx]) atomicAdd(&absacc[idx], s_abs[idx]);
+    if (argmax != nullptr) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            int best = 0;
+            double bv = dlink[(size_t)i * C] + linkfnull[0];
+            for (int c = 1; c < C; ++c) {
+                const double v = dlink[(size_t)i * C + c] + linkfnull[c];
+                if (v > bv) { bv = v; best = c; }
+            }
+            argmax[i] = best;
+        }
+    }
+}
+// mean |phi| per output and aggregated over outputs ([C + 1][Gp]) and their descending order (ties: higher index first,
+// what reversing a stable ascending argsort gives).  One block.
+__global__ void phi_rank_kernel(const unsigned long long* __restrict__ absacc, int C, int n, int Gp, double* __restrict__ mean_abs,
+                                int* __restrict__ order) {
+    for (int idx = threadIdx.x; idx < (C + 1) * Gp; idx += blockDim.x) {
+        const int r = idx / Gp, g = idx - r * Gp;
+        double v = 0.0;
+        if (r < C) v = from_fix((long long)absacc[r * Gp + g]) / (double)n;
+        else for (int c = 0; c < C; ++c) v += from_fix((long long)absacc[c * Gp + g]) / (double)n;
+        mean_abs[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (C + 1) * Gp; idx += blockDim.x) {
+        const int r = idx / Gp, g = idx - r * Gp;
+        const double v = mean_abs[idx];
+        int rank = 0;
+        for (int l = 0; l < Gp; ++l) {
+            const double o = mean_abs[r * Gp + l];
+            if (o > v || (o == v && l > g)) ++rank;
+        }
+        order[r * Gp + rank] = g;
+    }
+}
+
+// Cross-GPU completion of the push all-gather without a library barrier: every rank keeps a flag word per peer in
+// peer-mapped memory.  After the solve kernels (whose epilogues stored phi into the peers' buffers) one thread per peer
+// publishes this rank's step count into the peer's flag array (system-scope release) and waits until the peer's count has
+// reached the same step (acquire).  The step counter lives on the device, so a replayed CUDA graph keeps counting.
+struct PeerFlags {
+    unsigned long long* mine;            // [world] flags written by the peers
+    unsigned long long* peer[16];        // peer[r]: rank r's flag array, mapped here
+    unsigned long long* step;            // this rank's step counter (device memory)
+    int world, rank;
+};
+__global__ void peer_sync_kernel(PeerFlags f, int* __restrict__ status) {
+    __shared__ unsigned long long s_step;
+    if (threadIdx.x == 0) { s_step = *f.step + 1ull; *f.step = s_step; }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= f.world || t == f.rank) return;
+    const unsigned long long e = s_step;
+    __threadfence_system();              // everything this GPU stored before (previous kernels included) is ordered first
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.peer[t] + f.rank), "l"(e) : "memory");
+    unsigned long long seen = 0ull;
+    for (long long spins = 0; spins < (1ll << 31); ++spins) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f.mine + t) : "memory");
+        if (seen >= e) return;
+    }
+    if (atomicCAS(&status[0], 0, DKS_ERR_CUDA) == 0) status[1] = -78;     // a peer never arrived
+}
+
 // an instance list that must be empty (shapes no kernel covers): report instead of computing
 __global__ void flag_unsupported_kernel(const int* __restrict__ count, int detail, int* __restrict__ status) {
     if (*count > 0 && atomicCAS(&status[0], 0, DKS_ERR_UNSUPPORTED) == 0) status[1] = detail;

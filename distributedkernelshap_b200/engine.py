@@ -453,6 +453,16 @@ class GpuKernelExplainer:
         ptrs = np.asarray([int(p) for p in gathered_ptrs], dtype=np.uint64)
         _cabi.check(self.lib.dks_set_peers(self._ctx, int(world), int(rank), _cabi.ptr(ptrs), int(slab_doubles)))
 
+    def set_peer_flags(self, flag_ptrs):
+        """Multi-GPU: ``flag_ptrs[r]`` = device address (mapped here) of rank r's zero-initialised ``uint64[world]`` flag
+        array.  Every ``explain_device`` then ends with the engine's own cross-GPU signal / wait, so the gathered buffer is
+        complete when the stream reaches the next operation.  ``None`` switches it off."""
+        if flag_ptrs is None:
+            _cabi.check(self.lib.dks_set_peer_flags(self._ctx, None))
+            return
+        ptrs = np.asarray([int(p) for p in flag_ptrs], dtype=np.uint64)
+        _cabi.check(self.lib.dks_set_peer_flags(self._ctx, _cabi.ptr(ptrs)))
+
     def graph_launches(self):
         """How many ``explain_device`` calls were replayed as one CUDA-graph launch."""
         cnt = C.c_int64(0)

@@ -117,7 +117,7 @@ class PeerGather:
     (``torch.distributed._symmetric_memory``).  Raises if the process group / driver cannot provide peer mappings: callers
     fall back to ``all_gather_into_tensor``."""
 
-    def __init__(self, engine, C, n, G, device):
+    def __init__(self, engine, C, n, G, device, own_sync=True):
         import torch
         import torch.distributed._symmetric_memory as symm_mem
         dist = _dist()
@@ -128,9 +128,21 @@ class PeerGather:
         self.local = self.buffer[self.rank]                       # the solve writes this slab in place
         self.engine = engine
         engine.set_peers(self.world, self.rank, ptrs, C * n * G)
+        # the engine's own completion protocol: one flag word per peer in peer-mapped memory (signal + wait at the end of
+        # every explain call) instead of the symmetric-memory barrier
+        self.own_sync = False
+        if own_sync:
+            self.flags = symm_mem.empty((max(self.world, 2),), dtype=torch.int64, device=device)
+            self.flags.zero_()
+            self.flag_handle = symm_mem.rendezvous(self.flags, dist.group.WORLD)
+            torch.cuda.synchronize()
+            dist.barrier()                                        # every rank has zeroed its flags before anyone signals
+            engine.set_peer_flags([int(p) for p in self.flag_handle.buffer_ptrs])
+            self.own_sync = True
 
     def barrier(self):
-        self.handle.barrier(channel=0)
+        if not self.own_sync:                                     # with flags the explain call itself ends with the exchange
+            self.handle.barrier(channel=0)
 
     def close(self):
         self.engine.set_peers(0, 0, None, 0)

@@ -157,6 +157,12 @@ int dks_graph_launches(dks_ctx* ctx, int64_t* count);
  * reference's result collection (distributed.py:156-179) without NCCL; the caller completes it with a cross-GPU barrier.
  * Pass phi_dev = own buffer + rank * slab_doubles to have the solve write the local slab in place.  world <= 1 clears. */
 int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_ptrs_host, int64_t slab_doubles);
+/* Optional completion of that all-gather inside the engine: flag_ptrs_host[r] is the device address (mapped in THIS process) of
+ * rank r's flag array, uint64[world], zero-initialised (peer-mapped like the gathered buffers).  With flags set, every
+ * dks_run_dev ends with the engine's own cross-GPU signal/wait (one thread per peer, system-scope release/acquire): when the
+ * call's stream work is done, every peer's block has arrived in this rank's gathered buffer -- no library barrier needed.
+ * Call after dks_set_peers; NULL switches it off. */
+int dks_set_peer_flags(dks_ctx* ctx, const uint64_t* flag_ptrs_host);
 /* convenience: prepare + explain from/to host memory; H2D, kernels, D2H; synchronises.  This is the call a
  * non-torch host (ctypes / cgo) makes and the one bench.py's end-to-end number goes through. */
 int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
@@ -165,6 +171,13 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
  * synchronises): 0 ok, DKS_ERR_PLAN_MISSING, DKS_ERR_NUMERIC, DKS_ERR_UNSUPPORTED;
  * *detail = the offending M / instance index. */
 int dks_last_status(dks_ctx* ctx, int* detail);
+
+/* ---- post-processing of KernelShap.build_explanation off the resident phi (kernel_shap.py:36-109 rank_by_importance, :112-207
+ * sum_categories, :952-956 argmax) for the rows of the LAST dks_explain_host call: segment sums over consecutive groups
+ * (seg_offsets_host [Gp + 1], NULL = one segment per group, Gp = G), mean |phi| per output and aggregated over outputs
+ * ([C + 1][Gp]), their descending order, argmax of the raw prediction.  Output pointers may be NULL.  Synchronises. */
+int dks_summarise_host(dks_ctx* ctx, int n, const int32_t* seg_offsets_host, int Gp, double* phi_sum_host,
+                       double* mean_abs_host, int32_t* order_host, int32_t* argmax_host);
 
 /* ---- knobs / introspection ---------------------------------------------------------------------- */
 int dks_set_kernel(dks_ctx* ctx, int kernel);       /* DKS_KERNEL_* */
