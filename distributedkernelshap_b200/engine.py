@@ -361,6 +361,28 @@ class GpuKernelExplainer:
             _cabi.check(rc)
         return out if self.vector_out else out[:, 0]
 
+    def summarise(self, n, segments=None, want_sums=False):
+        """``KernelShap.build_explanation`` post-processing on the device, off the phi of the last host-path
+        ``shap_values`` call over ``n`` rows (kernel_shap.py:36-109, :112-207, :952-956): mean |phi| per output and
+        aggregated (``mean_abs`` [C + 1, Gp]), their descending order (``order``), the arg-max class of the raw prediction
+        (``argmax`` [n]) and, with ``segments`` (offsets of consecutive groups to add up: ``sum_categories``), the summed
+        shap values (``phi_sum`` [C, n, Gp]).  Returns None when the last call is not resident (row chunks, other calls)."""
+        if n != self._last_rows or self._link_fx_parts:
+            return None
+        G = self.data.groups_size
+        seg = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
+        Gp = G if seg is None else len(seg) - 1
+        mean_abs = np.zeros((self.D + 1, Gp))
+        order = np.zeros((self.D + 1, Gp), dtype=np.int32)
+        argmax = np.zeros(n, dtype=np.int32)
+        phi_sum = np.zeros((self.D, n, Gp)) if (want_sums and seg is not None) else None
+        rc = self.lib.dks_summarise_host(self._ctx, n, _cabi.ptr(seg), Gp, _cabi.ptr(phi_sum), _cabi.ptr(mean_abs),
+                                         _cabi.ptr(order), _cabi.ptr(argmax))
+        if rc == _cabi.DKS_ERR_INVALID:
+            return None
+        _cabi.check(rc)
+        return {"mean_abs": mean_abs, "order": order, "argmax": argmax, "phi_sum": phi_sum}
+
     def instance_plans(self):
         """Plans the device drew in the last ``plan_mode='per_instance'`` call: ``(zbits uint64[n, stride],
         w float64[n, stride])`` -- rows past an instance's S are zero.  For audits and tests."""

@@ -75,6 +75,35 @@ def rank_by_importance(shap_values: List[np.ndarray],
     return importances
 
 
+def category_segments(width: int, start_idx: Sequence[int], enc_feat_dim: Sequence[int]) -> np.ndarray:
+    """Offsets ``[0, ..., width]`` of the column segments ``sum_categories`` adds up (one per categorical variable, one per
+    remaining column): the form the device-side summary takes."""
+    block_len = dict(zip(start_idx, enc_feat_dim))
+    offsets, col = [], 0
+    while col < width:
+        offsets.append(col)
+        col += block_len.get(col, 1)
+    offsets.append(width)
+    return np.asarray(offsets, dtype=np.int32)
+
+
+def importances_from_device(summary: Dict, feature_names) -> Dict:
+    """``rank_by_importance`` output from the device-side summary (mean |phi| [C + 1, G'] and descending order)."""
+    mean_abs, order = summary['mean_abs'], summary['order']
+    n_feats = mean_abs.shape[1]
+    if not feature_names or len(feature_names) != n_feats:
+        if feature_names:
+            logger.warning(
+                "The feature names provided do not match the number of shap values estimated. "
+                "Received {} feature names but estimated {} shap values!".format(len(feature_names), n_feats))
+        feature_names = ['feature_{}'.format(i) for i in range(n_feats)]
+    out = {}
+    for r in range(mean_abs.shape[0]):
+        key = str(r) if r < mean_abs.shape[0] - 1 else 'aggregated'
+        out[key] = {'ranked_effect': mean_abs[r][order[r]], 'names': [feature_names[i] for i in order[r]]}
+    return out
+
+
 def sum_categories(values: np.ndarray, start_idx: Sequence[int], enc_feat_dim: Sequence[int]):
     """Sums, for every ``start_idx[i]``, the ``enc_feat_dim[i]`` consecutive columns starting there (the encoded levels
     of one categorical variable); other columns are kept.  Rank-3 inputs (interaction values) are reduced along both
@@ -429,11 +458,21 @@ class KernelShap(Explainer, FitMixin):
         # link(f(x)) was computed on the device by the explain call; the distributed explainer does not gather it
         getter = None if self.distribute else getattr(self._explainer, 'link_predictions', None)
         link_fx = getter() if getter is not None else None
+        # ranking / category sums / arg-max of build_explanation: one small kernel pair off the phi still resident on the GPU
+        device_summary = None
+        summariser = None if self.distribute else getattr(self._explainer, 'summarise', None)
+        if summariser is not None:
+            segments = None
+            if summarise_result and cat_vars_start_idx and cat_vars_enc_dim and not self.use_groups:
+                segments = category_segments(shap_values[0].shape[-1], cat_vars_start_idx, cat_vars_enc_dim)
+            device_summary = summariser(shap_values[0].shape[0] if shap_values[0].ndim == 2 else 1, segments=segments,
+                                        want_sums=segments is not None)
         return self.build_explanation(
             X,
             shap_values,
             expected_value,
             link_predictions=link_fx,
+            device_summary=device_summary,
             summarise_result=summarise_result,
             cat_vars_start_idx=cat_vars_start_idx,
             cat_vars_enc_dim=cat_vars_enc_dim,
@@ -446,8 +485,15 @@ class KernelShap(Explainer, FitMixin):
         summarise_result = kwargs.get('summarise_result', False)
         if summarise_result:
             self._check_result_summarisation(summarise_result, cat_vars_start_idx, cat_vars_enc_dim)
+        device_summary = kwargs.get('device_summary')
         if self.summarise_result:
-            shap_values = [sum_categories(arr, cat_vars_start_idx, cat_vars_enc_dim) for arr in shap_values]
+            if device_summary is not None and device_summary.get('phi_sum') is not None:
+                shap_values = [device_summary['phi_sum'][c] for c in range(len(shap_values))]
+            else:
+                device_summary = None                  # computed on unsummed groups: not what is being reported
+                shap_values = [sum_categories(arr, cat_vars_start_idx, cat_vars_enc_dim) for arr in shap_values]
+        elif device_summary is not None and device_summary['mean_abs'].shape[1] != np.atleast_2d(shap_values[0]).shape[1]:
+            device_summary = None
 
         # raw predictions on the scale the explainer works in (the reference wraps link.f in np.vectorize, an
         # interpreted per-element loop; both links are NumPy ufunc expressions, so they are applied to the array)
@@ -455,8 +501,12 @@ class KernelShap(Explainer, FitMixin):
         if raw_predictions is None:
             raw_predictions = convert_to_link(self.link).f(np.asarray(self.predictor(X), dtype=np.float64))
 
-        argmax_pred = np.argmax(np.atleast_2d(raw_predictions), axis=1) if self.task != 'regression' else []
-        importances = rank_by_importance(shap_values, feature_names=self.feature_names)
+        if device_summary is not None and len(shap_values) + 1 == device_summary['mean_abs'].shape[0]:
+            argmax_pred = device_summary['argmax'] if self.task != 'regression' else []
+            importances = importances_from_device(device_summary, self.feature_names)
+        else:
+            argmax_pred = np.argmax(np.atleast_2d(raw_predictions), axis=1) if self.task != 'regression' else []
+            importances = rank_by_importance(shap_values, feature_names=self.feature_names)
 
         X = X.toarray() if (isinstance(X, sparse.spmatrix) or sparse.issparse(X)) else np.array(X)
 
