@@ -56,6 +56,7 @@ def parse_args():
                          "plan per instance drawn on the GPU (what shap does on the CPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-oracle timing")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the secondary leg (the other plan mode)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the bounded runs of BASELINE configs[2]-[4]")
     ap.add_argument("--cpu-sample", type=int, default=16, help="instances the CPU baseline explains")
     return ap.parse_args()
 
@@ -283,6 +284,67 @@ def measure_mode(wl, X, plan_mode, kernel, steps, warmup, flush, stream):
     return out
 
 
+OTHER_CONFIGS = {
+    "configs[2]": dict(label="synthetic dense tabular: 64 features (ungrouped), bg=512, nsamples=4096, LR (BASELINE.json "
+                             "configs[2]; 16384 of its 1M instances)", kind="dense", features=64, bg=512, ns=4096),
+    "configs[3] grouped": dict(label="wide one-hot, grouped reading: 64 variables x 16 levels = 1024 columns, bg=256, "
+                                     "nsamples=8192 (BASELINE.json configs[3]; 8192 of its 100k instances; the 1024-singleton "
+                                     "reading needs > 128 groups and is refused)", kind="onehot", features=1024, bg=256, ns=8192),
+    "configs[4] one GPU": dict(label="synthetic: 128 features (two-word coalition rows), bg=512, nsamples=4096 (BASELINE.json "
+                                     "configs[4]; 16384 instances = a slice of one GPU's share of the 10M)", kind="dense",
+                               features=128, bg=512, ns=4096),
+}
+
+
+def measure_config(name, spec, flush, stream, steps=3, warmup=1):
+    """Throughput of one of the other BASELINE.json configs at a bounded instance count on one GPU (shared plans): device
+    resident (CUDA events, L2 flushed between steps), through the host API with l1_reg=False, and through the host API with
+    the reference's DEFAULT kwargs (l1_reg='auto': LassoLarsIC feature selection on the device, csrc/dks_l1.cuh)."""
+    import torch
+    from distributedkernelshap_b200.data import DenseData
+    from distributedkernelshap_b200.datasets import dense_tabular, wide_onehot
+    from distributedkernelshap_b200.engine import GpuKernelExplainer
+    n = 8192 if spec["kind"] == "onehot" else 16384
+    wl = dense_tabular(n, spec["features"], spec["bg"], seed=0) if spec["kind"] == "dense" else \
+        wide_onehot(n, 64, 16, spec["bg"], seed=0)
+    X = np.ascontiguousarray(wl["X_explain"])
+    eng = GpuKernelExplainer(wl["predictor"].predict_proba, DenseData(wl["background"], wl["group_names"], wl["groups"]),
+                             link="logit", seed=0)
+    G = len(wl["groups"])
+    eng.shap_values(X[:512], nsamples=spec["ns"], l1_reg=False)              # plans built + uploaded
+    eng.set_stream(stream.cuda_stream)
+    X_dev = torch.from_numpy(X).cuda()
+    phi = torch.empty((2, n, G), dtype=torch.float64, device="cuda")
+    ms = []
+    for k in range(warmup + steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.explain_device(X_dev.data_ptr(), n, phi.data_ptr(), nsamples=spec["ns"])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if k >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    eng.check_status()
+    out = {"workload": spec["label"], "instances": n, "plan": "shared per M", "value": n / (statistics.mean(ms) / 1e3),
+           "unit": "instances/s", "ms_per_step": statistics.mean(ms)}
+    t0 = time.perf_counter()
+    eng.shap_values(X, nsamples=spec["ns"], l1_reg=False)
+    out["e2e"] = {"value": n / (time.perf_counter() - t0), "unit": "instances/s", "l1_reg": False}
+    n1 = 2048
+    try:
+        eng.shap_values(X[:64], nsamples=spec["ns"])                          # l1 tables uploaded
+        t0 = time.perf_counter()
+        sv = eng.shap_values(X[:n1], nsamples=spec["ns"])                     # reference default: l1_reg='auto'
+        out["e2e_reference_default_kwargs"] = {
+            "value": n1 / (time.perf_counter() - t0), "unit": "instances/s", "instances": n1, "l1_reg": "auto (LassoLarsIC aic)",
+            "mean_features_selected": float(np.count_nonzero(sv[1], axis=1).mean())}
+    except Exception as exc:                                                  # pragma: no cover - reported, not hidden
+        out["e2e_reference_default_kwargs"] = {"error": repr(exc)[:300]}
+    eng.close()
+    return out
+
+
 PLAN_LABEL = {"shared": "shared per M (one plan for every instance with M varying groups; the engine's fast mode)",
               "per_instance": "per instance, drawn on the GPU (Philox keyed by seed and global row: what shap does on the CPU)"}
 
@@ -455,6 +517,16 @@ def run_ours(args):
         other_mode = "per_instance" if args.plan_mode == "shared" else "shared"
         other = measure_mode(wl, X, other_mode, args.kernel, args.steps, args.warmup, flush, stream)
 
+    # ---------------- the other BASELINE.json configs at a bounded size (coverage data points in the same record) --------
+    other_configs = None
+    if world == 1 and not args.no_other_configs:
+        other_configs = {}
+        for cname, spec in OTHER_CONFIGS.items():
+            try:
+                other_configs[cname] = measure_config(cname, spec, flush, stream)
+            except Exception as exc:                                          # pragma: no cover
+                other_configs[cname] = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -511,6 +583,8 @@ def run_ours(args):
         line["sustained"] = sustained
     if other is not None:
         line["per_instance" if args.plan_mode == "shared" else "shared_plan"] = other
+    if other_configs is not None:
+        line["other_configs"] = other_configs
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
     print(json.dumps(line))

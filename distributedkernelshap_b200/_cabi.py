@@ -72,6 +72,8 @@ SIGNATURES = {
     "dks_explain_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dks_explain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dks_summarise_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dks_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "dks_host_free": (C.c_int, [C.c_void_p]),
     "dks_last_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "dks_set_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "dks_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -271,7 +271,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     }
     const bool fused = fast && !l1 && ctx->opt_fused && pg.pmat64 != nullptr && pg.W == 1 &&
                        dks::shared_path::fused_config(ctx->N, G, pg.S_pad, ctx->sm_count, ctx->max_smem_optin,
-                                                      ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
+                                                      ctx->opt_fused_ni, ctx->opt_fused_warps, ctx->opt_fused_B, &fcfg);
     ctx->last_fused = fused;
     if (fused) {
         // link + projection solve inside the coalition kernel: no (sum p1, sum p0) buffer, no separate solve launch
@@ -1169,16 +1169,23 @@ int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host
     ctx->phi_rows = n;                      // dks_summarise_host works off this buffer
     // results travel through a pinned staging buffer: one asynchronous DMA + one host memcpy instead of the driver's
     // chunked pageable path (the caller's array is ordinary NumPy memory)
-    if (need_phi > ctx->cap_phi_pin) {
+    bool direct = false;                    // the caller's array is page-locked: one DMA straight into it
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, phi_host) == cudaSuccess) direct = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    if (!direct && need_phi > ctx->cap_phi_pin) {
         if (ctx->h_phi_pin) cudaFreeHost(ctx->h_phi_pin);
         ctx->h_phi_pin = nullptr; ctx->cap_phi_pin = 0;
         CUDA_TRY(cudaHostAlloc((void**)&ctx->h_phi_pin, sizeof(double) * need_phi, cudaHostAllocDefault));
         ctx->cap_phi_pin = need_phi;
     }
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_phi_pin, ctx->d_phi, sizeof(double) * need_phi, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(direct ? phi_host : ctx->h_phi_pin, ctx->d_phi, sizeof(double) * need_phi, cudaMemcpyDeviceToHost,
+                             ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    memcpy(phi_host, ctx->h_phi_pin, sizeof(double) * need_phi);
+    if (!direct) memcpy(phi_host, ctx->h_phi_pin, sizeof(double) * need_phi);
     return check_status(ctx);
 }
 
@@ -1222,6 +1229,17 @@ int dks_summarise_host(dks_ctx* ctx, int n, const int32_t* seg_offsets_host, int
     cudaFree(d_abs); cudaFree(d_mean); cudaFree(d_ord); cudaFree(d_arg);
     if (d_seg) cudaFree(d_seg);
     if (d_sum) cudaFree(d_sum);
+    return DKS_OK;
+}
+
+int dks_host_alloc(void** out, uint64_t bytes) {
+    if (!out || bytes == 0) return fail(DKS_ERR_INVALID, "dks_host_alloc: bad arguments");
+    CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return DKS_OK;
+}
+
+int dks_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
     return DKS_OK;
 }
 

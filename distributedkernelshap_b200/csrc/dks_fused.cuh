@@ -71,7 +71,7 @@ inline size_t fused_smem_bytes(int warps, int kpad, int B) {
 
 // NCT: background rows at compile time (0 = run-time p.N): with NCT the chunk loop unrolls completely (static tensor-memory
 // offsets, no loop control, the tail folded).  B (instances parked per warp) is a power of two.
-template <int NCT, int KPAD, int NWARPS>
+template <int NCT, int KPAD, int NWARPS, int NI>
 __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(FusedParams p, int warps_used, int cstride) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ uint32_t s_tmem;
@@ -212,40 +212,62 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
         const double* xb2 = p.XT + (ntab > 2 ? 32 + (int)((zz >> 8) & 15ull) : 0);
         const double* xb3 = p.XT + (ntab > 3 ? 48 + (int)((zz >> 12) & 15ull) : 0);
         const int last_it = my_n > 0 ? my_n - 1 : 0;
-        int i_nx = my_n > 0 ? p.list[part + (1 < my_n ? 1 : 0) * nparts] : 0;
-        double nx0 = 0.0, nx1 = 0.0, nx2 = 0.0, nx3 = 0.0;
-        if (my_n > 0) {
-            const size_t o = (size_t)p.list[part] * xstride;
-            nx0 = __ldg(xb0 + o); nx1 = __ldg(xb1 + o); nx2 = __ldg(xb2 + o); nx3 = __ldg(xb3 + o);
+        // NI instances share one pass over the warp's rows of tensor memory: instance ordinals it .. it + NI - 1
+        int i_nx[NI];
+        double nx[NI][4];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int o0 = u < last_it ? u : last_it, o1 = NI + u < last_it ? NI + u : last_it;
+            i_nx[u] = my_n > 0 ? p.list[part + o1 * nparts] : 0;
+            nx[u][0] = nx[u][1] = nx[u][2] = nx[u][3] = 0.0;
+            if (my_n > 0) {
+                const size_t o = (size_t)p.list[part + o0 * nparts] * xstride;
+                nx[u][0] = __ldg(xb0 + o); nx[u][1] = __ldg(xb1 + o); nx[u][2] = __ldg(xb2 + o); nx[u][3] = __ldg(xb3 + o);
+            }
         }
 
-        for (int it = 0; it < my_n; ++it) {
-            const double a = ((nx0 + nx1) + (nx2 + nx3)) + es;
-            {
-                const size_t o = (size_t)i_nx * xstride;
-                nx0 = __ldg(xb0 + o); nx1 = __ldg(xb1 + o); nx2 = __ldg(xb2 + o); nx3 = __ldg(xb3 + o);
-                const int it2 = it + 2 < last_it ? it + 2 : last_it;
-                i_nx = p.list[part + it2 * nparts];
+        for (int it = 0; it < my_n; it += NI) {
+            float A[NI];
+            bool risky_l = false;
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                const double a = ((nx[u][0] + nx[u][1]) + (nx[u][2] + nx[u][3])) + es;
+                {
+                    const size_t o = (size_t)i_nx[u] * xstride;
+                    nx[u][0] = __ldg(xb0 + o); nx[u][1] = __ldg(xb1 + o); nx[u][2] = __ldg(xb2 + o); nx[u][3] = __ldg(xb3 + o);
+                    const int it2 = it + 2 * NI + u < last_it ? it + 2 * NI + u : last_it;
+                    i_nx[u] = p.list[part + it2 * nparts];
+                }
+                // A = 2^a = 2^n 2^f, n = rint(a) through the 1.5 * 2^52 trick (no conversion instructions), |f| <= 1/2; the
+                // exponent is clamped to [-120, 120] (saturated scores; the clamped scalar path below takes A > 1e18)
+                const double tm = a + 6755399441055744.0;
+                int an_i = __double2loint(tm);
+                an_i = an_i < -120 ? -120 : (an_i > 120 ? 120 : an_i);
+                A[u] = ex2_approx((float)(a - (tm - 6755399441055744.0))) * __int_as_float((127 + an_i) << 23);
+                risky_l = risky_l || A[u] > 1.0e18f;
             }
-            // A = 2^a = 2^n 2^f, n = rint(a) through the 1.5 * 2^52 trick (no conversion instructions), |f| <= 1/2; the
-            // exponent is clamped to [-120, 120] (saturated scores; the clamped scalar path below takes A > 1e18)
-            const double tm = a + 6755399441055744.0;
-            int an_i = __double2loint(tm);
-            an_i = an_i < -120 ? -120 : (an_i > 120 ? 120 : an_i);
-            const float A = ex2_approx((float)(a - (tm - 6755399441055744.0))) * __int_as_float((127 + an_i) << 23);
-            float s1, s0;
-            if (__any_sync(0xffffffffu, A > 1.0e18f)) {
+            float s1[NI], s0[NI];
+            if (__any_sync(0xffffffffu, risky_l)) {
                 // A^2 would leave the fp32 range: clamped scalar path on the raw row from global memory (saturated scores)
-                float r1 = 0.f, r0 = 0.f;
-                for (int j = 0; j + 1 < N; j += 2)
-                    pair_acc<true>(A, p.DmT[(size_t)j * p.S_pad + s], p.DmT[(size_t)(j + 1) * p.S_pad + s], r1, r0);
-                if (N & 1) single_acc(A, p.DmT[(size_t)(N - 1) * p.S_pad + s], r1, r0);
-                s1 = r1; s0 = r0;
+#pragma unroll
+                for (int u = 0; u < NI; ++u) {
+                    float r1 = 0.f, r0 = 0.f;
+                    for (int j = 0; j + 1 < N; j += 2)
+                        pair_acc<true>(A[u], p.DmT[(size_t)j * p.S_pad + s], p.DmT[(size_t)(j + 1) * p.S_pad + s], r1, r0);
+                    if (N & 1) single_acc(A[u], p.DmT[(size_t)(N - 1) * p.S_pad + s], r1, r0);
+                    s1[u] = r1; s0[u] = r0;
+                }
             } else {
-                const float AA = A * A;
-                const f32x2 A2 = f2_pack(A, A), AA2 = f2_pack(AA, AA), AA2x2 = f2_pack(2.f * AA, 2.f * AA);
-                f32x2 acc1[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)}, acc0[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
-                float t1s = 0.f, t0s = 0.f;
+                f32x2 A2[NI], AA2[NI], AA2x2[NI];
+                f32x2 acc1[NI][2], acc0[NI][2];
+                float t1s[NI], t0s[NI];
+#pragma unroll
+                for (int u = 0; u < NI; ++u) {
+                    const float AA = A[u] * A[u];
+                    A2[u] = f2_pack(A[u], A[u]); AA2[u] = f2_pack(AA, AA); AA2x2[u] = f2_pack(2.f * AA, 2.f * AA);
+                    acc1[u][0] = acc1[u][1] = acc0[u][0] = acc0[u][1] = f2_pack(0.f, 0.f);
+                    t1s[u] = t0s[u] = 0.f;
+                }
                 float v[2][16];
                 tc::tmem_ld16(taddr, v[0]);
 #pragma unroll
@@ -253,27 +275,39 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
                     if (c < nch) {
                         tc::tmem_ld_wait(v[c & 1]);
                         if (c + 1 < nch) tc::tmem_ld16(taddr + (c + 1) * 16, v[(c + 1) & 1]);
-                        if (c < nfull) chunk_sums<16>(v[c & 1], A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
-                        else chunk_sums_rt(v[c & 1], nq_t, rem_t, A, A2, AA2, AA2x2, one2, two2, acc1, acc0, t1s, t0s);
+#pragma unroll
+                        for (int u = 0; u < NI; ++u) {
+                            if (c < nfull) chunk_sums<16>(v[c & 1], A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
+                            else chunk_sums_rt(v[c & 1], nq_t, rem_t, A[u], A2[u], AA2[u], AA2x2[u], one2, two2, acc1[u], acc0[u], t1s[u], t0s[u]);
+                        }
                     }
                 }
-                float q0, q1, q2, q3;
-                f2_unpack(f2_add(acc1[0], acc1[1]), q0, q1);
-                f2_unpack(f2_add(acc0[0], acc0[1]), q2, q3);
-                s1 = (q0 + q1) + t1s;
-                s0 = (q2 + q3) + t0s;
+#pragma unroll
+                for (int u = 0; u < NI; ++u) {
+                    float q0, q1, q2, q3;
+                    f2_unpack(f2_add(acc1[u][0], acc1[u][1]), q0, q1);
+                    f2_unpack(f2_add(acc0[u][0], acc0[u][1]), q2, q3);
+                    s1[u] = (q0 + q1) + t1s[u];
+                    s0[u] = (q2 + q3) + t0s[u];
+                }
             }
-            // ---- link in place, row parked for the turn-around
-            double y = 0.0;
-            if (row_ok) {
-                if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(s1, s0, s_logtab) - lf1;
-                else y = (double)s1 * inv_n - f1;
+            // ---- link in place, rows parked for the turn-around (B is a multiple of NI: a pass never straddles a batch)
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                if (it + u < my_n) {
+                    double y = 0.0;
+                    if (row_ok) {
+                        if (p.link == DKS_LINK_LOGIT) y = fast_log_ratio(s1[u], s0[u], s_logtab) - lf1;
+                        else y = (double)s1[u] * inv_n - f1;
+                    }
+                    sYw[lane * ystride + ((it + u) & bmask)] = y;
+                }
             }
-            const int slot = it & bmask;
-            sYw[lane * ystride + slot] = y;
-            if (slot == bmask || it == my_n - 1) {
+            const int last_done = it + NI - 1 < last_it ? it + NI - 1 : last_it;      // last ordinal this pass completed
+            const int slot = last_done & bmask;
+            if (slot == bmask || last_done == last_it) {
                 __syncwarp();
-                flush(it - slot, slot + 1);
+                flush(last_done - slot, slot + 1);
                 __syncwarp();
             }
         }
@@ -322,7 +356,8 @@ struct FusedConfig { int ni, warps, B, slices; size_t smem; };
 
 // picks (warps per CTA, batch) for a shape; returns false when the fused kernel does not apply.
 // want_warps / want_B: 0 = default (tuning knobs, dks_set_option)
-inline bool fused_config(int N, int G, int S_pad, int sm_count, int max_smem, int want_warps, int want_B, FusedConfig* cfg) {
+inline bool fused_config(int N, int G, int S_pad, int sm_count, int max_smem, int want_ni, int want_warps, int want_B,
+                         FusedConfig* cfg) {
     if (G < 2 || G > 16 || N > MAXN) return false;                        // at most four nibble tables, 15 coefficients
     const int cstride = (N + 3) / 4 * 4, reach = (N + 15) / 16 * 16;
     int slices = 5;
@@ -330,12 +365,12 @@ inline bool fused_config(int N, int G, int S_pad, int sm_count, int max_smem, in
     int warps = 4 * slices;
     if (want_warps == 16 && warps > 16) warps = 16;
     const int kpad = fused_kpad(G);
-    int B = 32;
-    if (want_B == 16 || want_B == 8) B = want_B;
+    int B = 16;                                    // measured best on B200 (a smaller staging tile leaves more L1 to the table loads)
+    if (want_B == 32 || want_B == 8) B = want_B;
     while (B > 8 && fused_smem_bytes(warps, kpad, B) + 1024 > (size_t)max_smem) B >>= 1;
     if (fused_smem_bytes(warps, kpad, B) + 1024 > (size_t)max_smem) return false;
     if ((long long)sm_count * warps < S_pad / 32) return false;          // every row group needs a warp
-    cfg->ni = 1;
+    cfg->ni = (want_ni == 2 && fused_kpad(G) == 12) ? 2 : 1;          // two instances per tensor-memory pass (tuning knob)
     cfg->warps = warps; cfg->B = B; cfg->slices = warps / 4;
     cfg->smem = fused_smem_bytes(warps, kpad, B);
     return true;
@@ -345,26 +380,30 @@ inline cudaError_t launch_explain_fused(const FusedParams& p, const FusedConfig&
     const int kpad = fused_kpad(p.G);
     const int cstride = (p.N + 3) / 4 * 4;
     cudaError_t err = cudaSuccess;
-#define DKS_FUSED_LAUNCH(NCT, KP, NW)                                                                                 \
+#define DKS_FUSED_LAUNCH(NCT, KP, NW, NI)                                                                             \
     do {                                                                                                              \
-        err = cudaFuncSetAttribute(explain_shared_fused_kernel<NCT, KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        err = cudaFuncSetAttribute(explain_shared_fused_kernel<NCT, KP, NW, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)cfg.smem);                                                                    \
         if (err == cudaSuccess)                                                                                       \
-            explain_shared_fused_kernel<NCT, KP, NW><<<grid, 32 * NW, cfg.smem, stream>>>(p, cfg.warps, cstride);    \
+            explain_shared_fused_kernel<NCT, KP, NW, NI><<<grid, 32 * NW, cfg.smem, stream>>>(p, cfg.warps, cstride); \
     } while (0)
     // background sizes with a compile-time specialisation (the chunk loop unrolls completely); everything else takes the
     // run-time version
     const int nw = cfg.warps > 16 ? 20 : 16;
-    if (kpad == 12) {
-        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 12, 20);
-        else if (p.N == 128 && nw == 16) DKS_FUSED_LAUNCH(128, 12, 16);
-        else if (p.N == 64 && nw == 20) DKS_FUSED_LAUNCH(64, 12, 20);
-        else if (nw == 20) DKS_FUSED_LAUNCH(0, 12, 20);
-        else DKS_FUSED_LAUNCH(0, 12, 16);
+    if (kpad == 12 && cfg.ni == 2) {
+        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 12, 20, 2);
+        else if (nw == 20) DKS_FUSED_LAUNCH(0, 12, 20, 2);
+        else DKS_FUSED_LAUNCH(0, 12, 16, 2);
+    } else if (kpad == 12) {
+        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 12, 20, 1);
+        else if (p.N == 128 && nw == 16) DKS_FUSED_LAUNCH(128, 12, 16, 1);
+        else if (p.N == 64 && nw == 20) DKS_FUSED_LAUNCH(64, 12, 20, 1);
+        else if (nw == 20) DKS_FUSED_LAUNCH(0, 12, 20, 1);
+        else DKS_FUSED_LAUNCH(0, 12, 16, 1);
     } else {
-        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 16, 20);
-        else if (nw == 20) DKS_FUSED_LAUNCH(0, 16, 20);
-        else DKS_FUSED_LAUNCH(0, 16, 16);
+        if (p.N == 100 && nw == 20) DKS_FUSED_LAUNCH(100, 16, 20, 1);
+        else if (nw == 20) DKS_FUSED_LAUNCH(0, 16, 20, 1);
+        else DKS_FUSED_LAUNCH(0, 16, 16, 1);
     }
 #undef DKS_FUSED_LAUNCH
     return err;

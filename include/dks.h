@@ -167,6 +167,11 @@ int dks_set_peer_flags(dks_ctx* ctx, const uint64_t* flag_ptrs_host);
  * non-torch host (ctypes / cgo) makes and the one bench.py's end-to-end number goes through. */
 int dks_explain_host(dks_ctx* ctx, const double* X_host, int n, double* phi_host, const uint64_t* ext_zbits_host,
                      const double* ext_w_host, int ext_stride);
+/* Page-locked host memory for result arrays (optional).  When the phi_host handed to dks_explain_host lies in page-locked
+ * memory (allocated here, or registered by the caller) the shap values arrive by ONE asynchronous DMA; pageable memory goes
+ * through the library's pinned staging buffer and a host memcpy. */
+int dks_host_alloc(void** out, uint64_t bytes);
+int dks_host_free(void* p);
 /* status of the LAST explain call on this context (the asynchronous calls leave it on the device; this fetches it and
  * synchronises): 0 ok, DKS_ERR_PLAN_MISSING, DKS_ERR_NUMERIC, DKS_ERR_UNSUPPORTED;
  * *detail = the offending M / instance index. */

@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -60 | te
 echo "== smoke"; timeout 300 python __graft_entry__.py 2>&1 | tail -3 | tee $OUT/smoke.log
 run_bench() {
   name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-mode 2>&1 | tail -1 > $OUT/bench_$name.json
+  env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-mode --no-other-configs 2>&1 | tail -1 > $OUT/bench_$name.json
   python - <<PY
 import json
 try:
@@ -26,7 +26,7 @@ echo "== full default bench line (both plan modes, cpu baseline)"
 timeout 600 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 > $OUT/bench_default.json; cut -c1-600 $OUT/bench_default.json
 echo "== ncu full capture of the fused kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:explain_shared_fused -s 2 -c 1 -f -o $OUT/prof_fused \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-mode > $OUT/ncu_full_stdout.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-mode --no-other-configs > $OUT/ncu_full_stdout.log 2>&1
 echo "== compute-sanitizer memcheck (smoke)"
 timeout 900 compute-sanitizer --tool memcheck --log-file $OUT/sanitizer_memcheck.log python __graft_entry__.py > $OUT/sanitizer_memcheck_stdout.log 2>&1
 tail -4 $OUT/sanitizer_memcheck.log; tail -2 $OUT/sanitizer_memcheck_stdout.log
