@@ -106,6 +106,11 @@ int ensure_workspace(dks_ctx* ctx, int n) {
 // timing events: inside a stream capture they become external event-record nodes, so dks_last_timings keeps working
 // for graph launches
 cudaError_t record_ev(dks_ctx* ctx, int k) {
+    if (ctx->capturing && !ctx->opt_graph_timing) {   // four event-record nodes cost a replayed graph several microseconds
+        ctx->timing_valid = false;
+        return cudaSuccess;
+    }
+    if (k == 0) ctx->timing_valid = true;
     return cudaEventRecordWithFlags(ctx->ev[k], ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
@@ -114,6 +119,7 @@ int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
     TRY(ensure_workspace(ctx, n));
     // histogram, status word and list counters are adjacent: one memset
     CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4), ctx->stream));
+    if (!ctx->capturing) ctx->last_was_graph = false;
     CUDA_TRY(record_ev(ctx, 0));
     int ipb = 256 / G;
     if (ipb < 1) ipb = 1;
@@ -1058,6 +1064,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
         CUDA_TRY(cudaGraphLaunch(ctx->gexec, ctx->stream));
         ctx->graph_launches++;
         ctx->launches += ctx->graph_kernels;
+        ctx->last_was_graph = true;
         return DKS_OK;                          // the status word stays on the device until dks_last_status asks for it
     }
     // the second identical call is captured (the first one sized every workspace, so nothing allocates during capture)
@@ -1080,6 +1087,7 @@ int dks_run_dev(dks_ctx* ctx, const double* X_dev, int n, double* phi_dev) {
     if (rc == DKS_OK) rc = launch_explain(ctx, phi_dev, nullptr, nullptr, 0);
     if (rc == DKS_OK) rc = launch_push(ctx, phi_dev);
     if (rc == DKS_OK) rc = launch_peer_sync(ctx);
+    ctx->last_was_graph = capture;          // the captured sequence runs as a graph launch below
     if (capture) {
         ctx->capturing = false;
         cudaGraph_t graph = nullptr;
@@ -1260,6 +1268,7 @@ int dks_set_option(dks_ctx* ctx, const char* name, int value) {
     else if (key == "fused_batch") ctx->opt_fused_B = value;
     else if (key == "push_in_kernel") ctx->push_in_kernel = value != 0;
     else if (key == "graph") ctx->graph_enabled = value != 0;
+    else if (key == "graph_timing") ctx->opt_graph_timing = value != 0;
     else return fail(DKS_ERR_INVALID, "dks_set_option: unknown option '%s'", name);
     ctx->epoch++;                      // a captured graph holds the old launch sequence
     return DKS_OK;
@@ -1280,6 +1289,8 @@ int dks_kernel_launches(dks_ctx* ctx, int64_t* count) {
 int dks_last_timings(dks_ctx* ctx, float* ms3) {
     BIND(ctx);
     REQUIRE(ms3 && ctx->prepared, "dks_last_timings: nothing to report");
+    REQUIRE(ctx->timing_valid && !(ctx->last_was_graph && !ctx->opt_graph_timing),
+            "dks_last_timings: the last call was a graph replay without timing nodes (dks_set_option \"graph_timing\" 1, or \"graph\" 0)");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaEventElapsedTime(&ms3[0], ctx->ev[0], ctx->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&ms3[1], ctx->ev[2], ctx->ev[3]));

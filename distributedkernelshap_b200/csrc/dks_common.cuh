@@ -208,6 +208,8 @@ struct dks_ctx {
     bool push_in_kernel = true;                    // the solve epilogues store phi into the peers' buffers themselves
     // tuning knobs (dks_set_option; defaults from the environment at dks_create: DKS_FUSED, DKS_FUSED_NI, ...)
     int opt_fused = 1, opt_fused_ni = 0, opt_fused_warps = 0, opt_fused_B = 0;
+    bool opt_graph_timing = false;   // keep the timing event records inside a captured graph (dks_last_timings after replays)
+    bool timing_valid = false, last_was_graph = false;
     bool last_fused = false;                       // the last explain ran the fused shared-plan kernel
 
     // the general kernel for the instances the shared-plan path does not take runs on a side stream, next to the fused kernel

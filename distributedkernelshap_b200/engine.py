@@ -23,39 +23,6 @@ MODEL_CHECK_RTOL = 1e-9
 MAX_ROWS_PER_CALL = 65536     # rows per C-ABI call: bounds the engine's per-call workspace (n x S x 8 B on the fast path)
 
 
-class _PinnedPool:
-    """Page-locked result arrays (``dks_host_alloc``), recycled by size: the D2H copy of the shap values lands straight in the
-    array the caller receives (no staging memcpy).  A buffer returns to the pool when the last NumPy view of it is gone; past
-    ``MAX_BYTES`` of page-locked memory in flight, ordinary arrays are handed out instead."""
-    MAX_BYTES = 256 << 20
-
-    def __init__(self, lib):
-        self.lib = lib
-        self.free = {}
-        self.bytes = 0
-
-    def array(self, shape):
-        import weakref
-        count = int(np.prod(shape))
-        nbytes = count * 8
-        ptr = None
-        if self.free.get(nbytes):
-            ptr = self.free[nbytes].pop()
-        elif self.bytes + nbytes <= self.MAX_BYTES:
-            out = C.c_void_p()
-            if self.lib.dks_host_alloc(C.byref(out), nbytes) == 0:
-                ptr = out.value
-                self.bytes += nbytes
-        if ptr is None:
-            return np.empty(shape)
-        raw = (C.c_double * count).from_address(ptr)
-        weakref.finalize(raw, self._release, nbytes, ptr)
-        return np.frombuffer(raw, dtype=np.float64).reshape(shape)
-
-    def _release(self, nbytes, ptr):
-        self.free.setdefault(nbytes, []).append(ptr)
-
-
 class GpuKernelExplainer:
     """CUDA KernelSHAP explainer with the interface of ``shap.KernelExplainer`` / ``KernelExplainerWrapper``.
 
@@ -132,7 +99,6 @@ class GpuKernelExplainer:
         self.expected_value = expected if self.vector_out else float(expected[0])
         self._nsamples_req = None
         self._plan_cache = {}
-        self._pinned = _PinnedPool(self.lib)
         self._l1_uploaded = {}
         self._l1_state = (0, 0, 0)
         self._link_fx_parts = []
@@ -146,7 +112,7 @@ class GpuKernelExplainer:
             return
         want = np.asarray(self.model_callable(bg), dtype=np.float64).reshape(self.N, -1)
         got = self.predict(bg)
-        if want.shape != got.shape or not np.allclose(got, want, rtol=1e-7, atol=1e-9):
+        if want.shape != got.shape or not np.allclose(got, want, rtol=1e-7, atol=1e-9, equal_nan=True):
             raise ValueError("the linear model extracted from `predictor` does not reproduce predictor(background): "
                              "refusing to explain a different function (max abs diff "
                              f"{np.max(np.abs(got - want)) if want.shape == got.shape else 'shape mismatch'})")
@@ -339,7 +305,7 @@ class GpuKernelExplainer:
             self._last_rows = n
             return merged if self.vector_out else merged[0]
 
-        phi = self._pinned.array((self.D, n, G))    # the device writes every entry (zeros for groups that do not vary)
+        phi = np.empty((self.D, n, G))      # the device writes every entry (zeros for groups that do not vary)
         self._link_fx_parts = []
         if self.plan_mode == "per_instance":
             # the device draws each row's plan from (seed, global row index): tell it where this block starts

@@ -123,6 +123,30 @@ def test_varying_groups_isclose_rule():
         assert sorted(np.nonzero([(int(mask[i]) >> g) & 1 for g in range(3)])[0]) == sorted(vi), i
 
 
+def test_varying_groups_with_nan_columns():
+    """np.isclose(..., equal_nan=True): a NaN in x matches a NaN in the background.  Columns holding
+    NaNs take the full background scan on the device instead of the min / max shortcut."""
+    prob = make_problem(seed=16, n=6, N=7, widths=(1, 2, 1, 1))
+    bg, X = prob["bg"], prob["X"]
+    bg[:, 0] = np.nan                       # group 0: background all NaN
+    X[0, 0] = np.nan                        # equal to every background value: group 0 does not vary
+    X[1, 0] = 1.0                           # a number against NaNs: varies
+    bg[:, 3] = 2.0
+    bg[2, 3] = np.nan                       # group 2 (column 3): one NaN among constants
+    X[:, 3] = 2.0                           # differs from the NaN row only: varies
+    X[3, 3] = np.nan                        # NaN against mostly numbers: varies
+    bg[:, 4] = 5.0
+    X[:, 4] = 5.0                           # group 3 never varies
+    orc, eng = _oracle(prob), _engine(prob)
+    M, mask = eng.varying(X)
+    for i in range(X.shape[0]):
+        want = sorted(int(v) for v in orc.varying_groups(X[i:i + 1]))
+        got = [g for g in range(4) if (int(mask[i]) >> g) & 1]
+        assert got == want, (i, got, want)
+        assert M[i] == len(want)
+    assert not (int(mask[0]) & 1) and (int(mask[1]) & 1) and all((int(m) >> 2) & 1 for m in mask) and not any((int(m) >> 3) & 1 for m in mask)
+
+
 def test_identity_head_closed_form():
     """Affine model + identity link: phi_g = sum_{k in g} w_k (x_k - E_bg[bg_k]) exactly."""
     prob = make_problem(seed=7, n=12, N=9, widths=(1, 2, 1, 3, 1, 1, 2), weights=True)
