@@ -141,6 +141,31 @@ def reference_config(cores, per_worker):
                            "distributed.py:125 without ray)", "kernel": "cpu-oracle"}
 
 
+def usable_cores():
+    """Host cores this process may actually use: the CPU count, the scheduler affinity and the cgroup CPU quota, whichever is
+    smallest (a container that shows 128 CPUs under a 24-CPU quota runs 128 busy workers SLOWER than 24: measured on this
+    pool, scripts/cpu_scaling_probe.py)."""
+    import math
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, math.ceil(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, math.ceil(quota / period)))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; shap/ray are not installable offline) on all host
     cores, one single-threaded worker process per core like the ray ActorPool (distributed.py:125).  Workers build
@@ -149,7 +174,7 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_worker = 4
     ctx = mp.get_context("spawn")
     times = []
@@ -172,7 +197,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": reference_config(cores, per_worker),
             "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample,
-                             "blas_threads": _blas_threads()},
+                             "blas_threads": _blas_threads(), "cpu_count": os.cpu_count(),
+                             "cores_note": "cores = min(cpu count, scheduler affinity, cgroup CPU quota)"},
             "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
