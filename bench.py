@@ -528,6 +528,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         blocks.append(time.perf_counter() - t0)
     e2e_s = torch.tensor([statistics.median(blocks)], dtype=torch.float64, device="cuda")
+    # what came back through the host API is what the device-resident path computed (this rank's rows of the gathered result)
+    np.testing.assert_allclose(np.asarray(out[1])[rank * n:(rank + 1) * n], sv0[1], rtol=0, atol=1e-12)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(e2e_s.item())

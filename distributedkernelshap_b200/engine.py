@@ -287,6 +287,10 @@ class GpuKernelExplainer:
             raise ValueError(f"X has {X.shape[1]} columns, background has {self.P}")
         X = np.ascontiguousarray(X)
         n, G = X.shape[0], self.data.groups_size
+        if n == 0:                              # nothing to explain: empty arrays of the right shape (the C ABI wants n > 0)
+            self._last_rows = 0
+            empty = np.zeros((self.D, 0, G))
+            return [empty[c] for c in range(self.D)] if self.vector_out else empty[0]
         self._set_nsamples(nsamples)
         need_hist = self._l1_guard(l1_reg, nsamples)
 

@@ -83,3 +83,39 @@ def test_serving_backends_on_the_gpu():
     sv = np.asarray([o["data"]["shap_values"][1][0] for o in outs])
     ev = outs[0]["data"]["expected_value"][1]
     np.testing.assert_allclose(sv.sum(1) + ev, np.log(fx[:, 1] / fx[:, 0]), rtol=1e-7, atol=1e-7)
+
+
+def test_pool_of_gpus_matches_one_gpu_and_is_repeatable():
+    """Single process, several GPUs (the ActorPool pattern without ray): mini-batches handed to whichever worker is free.
+    With a seed every worker evaluates the same keyed shared plans, so the pooled result equals the sequential one and does
+    not depend on thread scheduling (sampled M: nsamples 2048 of 4094).  Needs two visible GPUs."""
+    from distributedkernelshap_b200 import parallel
+    from distributedkernelshap_b200.explainers.kernel_shap import KernelShap
+    if parallel.visible_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    d = _adult(300)
+    args = dict(link="logit", feature_names=d["group_names"], seed=5)
+    fkw = dict(group_names=d["group_names"], groups=d["groups"])
+    one = KernelShap(d["predictor"].predict_proba, **args)
+    one.fit(d["background"], **fkw)
+    want = one.explain(d["X_explain"], silent=True, nsamples=2048, l1_reg=False).shap_values
+    for trial in range(2):
+        pool = KernelShap(d["predictor"].predict_proba, distributed_opts={"n_cpus": 2, "batch_size": 37}, **args)
+        pool.fit(d["background"], **fkw)
+        assert len(pool._explainer.pool) == 2
+        got = pool.explain(d["X_explain"], silent=True, nsamples=2048, l1_reg=False).shap_values
+        np.testing.assert_array_equal(got[1], want[1])
+    few = KernelShap(d["predictor"].predict_proba, distributed_opts={"n_cpus": 2, "batch_size": None}, **args)
+    few.fit(d["background"], **fkw)
+    np.testing.assert_array_equal(few.explain(d["X_explain"][:1], silent=True, nsamples=2048, l1_reg=False).shap_values[1],
+                                  want[1][:1])                      # fewer rows than workers: no empty mini-batch
+
+
+def test_zero_rows():
+    from distributedkernelshap_b200.explainers.kernel_shap import KernelExplainerWrapper
+    d = _adult(4)
+    from distributedkernelshap_b200.data import DenseData
+    eng = KernelExplainerWrapper(d["predictor"].predict_proba, DenseData(d["background"], d["group_names"], d["groups"]),
+                                 link="logit", seed=0)
+    sv = eng.shap_values(d["X_explain"][:0], nsamples=2048, l1_reg=False)
+    assert len(sv) == 2 and sv[0].shape == (0, 12)
