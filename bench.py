@@ -211,8 +211,9 @@ class ClockSampler:
     region runs."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, device):
+    def __init__(self, device, interval=0.002):
         self.device = device
+        self.interval = interval
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -231,7 +232,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.interval)
 
     def start(self):
         try:
@@ -469,7 +470,7 @@ def run_ours(args):
     kernel_ms = []
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, interval=0.002 if world == 1 else 0.02)   # N ranks share the host's CPU quota
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -499,6 +500,7 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
     value = world * n / (ms_per_step / 1e3)
+    step_spread = {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)}     # this rank's steps
     np.testing.assert_allclose(phi_dev[1].cpu().numpy(), sv0[1], rtol=0, atol=1e-12)   # same values as the host path
 
     # ---------------- end to end through the plug-in with host buffers: `e2e` ----------------
@@ -597,22 +599,30 @@ def run_ours(args):
     elems = float(NSAMPLES) * N_BACKGROUND * n                   # sigmoid evaluations per launch (T_alg)
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     mufu_peak = 148 * 16 * sm_mhz * 1e6                          # MUFU ops/s at the observed clock (16 lanes/clk/SM, measured)
+    fused_names = "explain_shared_fused_kernel (shared-plan path: coalition sums + link + projection solve in one kernel; tcgen05 kernel on a side stream for partial varying sets)"
     kname, mufu_per_elem = {
-        "auto": ("explain_shared_tmem_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
-        "shared": ("explain_shared_tmem_kernel + wls_pmat_kernel (shared-plan fast path; tcgen05 kernel for partial varying sets)", 0.5),
+        "auto": (fused_names, 0.5), "shared": (fused_names, 0.5),
         "tcgen05": ("explain_tcgen05_kernel", 1.5), "simt": ("explain_simt_kernel", 2.0)}[engine.kernel]
     if args.plan_mode == "per_instance" and engine.kernel != "simt":
-        kname, mufu_per_elem = "sample_plans_kernel + explain_tcgen05_kernel (per-instance plans)", 1.5
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kname, "kernel_ms": k_ms, "peak_source": peak_src,
-                "note": "achieved = algorithmic bytes of the reference-shaped masked batch (4*S*N*D per instance, SURVEY "
-                        "§8d) / kernel time; the fused kernel never materialises that batch, so this is an EFFECTIVE "
-                        "fraction (> 1 is expected). The kernel's real bound is instruction issue / the MUFU pipe: see mufu_frac.",
-                "mufu_ops_per_elem": mufu_per_elem, "mufu_ops_per_s": mufu_per_elem * elems / (k_ms * 1e-3),
-                "mufu_frac": mufu_per_elem * elems / (k_ms * 1e-3) / mufu_peak}
+        kname, mufu_per_elem = "sample_plans_kernel + factor_plans_kernel + explain_tcgen05_kernel (per-instance plans)", 1.5
+    mufu_ops = mufu_per_elem * elems / (k_ms * 1e-3)
+    # The pipe that binds this stage is the MUFU (XU) pipe -- neither HBM nor the tensor pipe: `frac` is measured against
+    # it.  The effective-HBM figure SURVEY §8(d) defines (bytes of the reference-shaped masked batch / kernel time) is kept
+    # as a secondary field: the fused kernels never materialise that batch, so it exceeds the HBM peak by design.
+    roofline = {"bound": "mufu", "achieved": mufu_ops / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s (MUFU lane-ops)",
+                "frac": mufu_ops / mufu_peak, "traffic": traffic, "kernel": kname, "kernel_ms": k_ms,
+                "peak_source": "148 SMs x 16 MUFU lanes/clk (measured, profiles/r1_mufu_probe_b200.txt) x the SM clock sampled "
+                               "during the timed region",
+                "mufu_ops_per_elem": mufu_per_elem, "elems_per_launch": elems,
+                "effective_hbm": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                  "peak_source": peak_src,
+                                  "note": "algorithmic bytes of the masked batch (4*S*N*D per instance, SURVEY §8d) / kernel "
+                                          "time; an EFFECTIVE figure (> 1 expected): the batch is never materialised"},
+                "traffic_note": "dram__bytes_read + dram__bytes_write of the dominant kernel per launch, ncu --set full "
+                                "(profiles/roofline_traffic.json)"}
     if engine.kernel in ("auto", "shared") and args.plan_mode == "shared":
-        # shared-plan path: 7 packed fp32 ops (FFMA2/FMUL2/FADD2, two lanes each, half issue rate: measured,
-        # profiles/r1_ffma2_probe_b200.txt) per four sigmoids = 3.5 fp32 lane-ops per element against 128 lanes/clk/SM
+        # 7 packed fp32 ops (FFMA2/FMUL2/FADD2: two lanes each, two issue cycles) per four sigmoids = 3.5 fp32 lane-ops per
+        # element against 128 lanes/clk/SM
         fp32_peak = 148 * 128 * sm_mhz * 1e6
         roofline.update({"fp32_lane_ops_per_elem": 3.5, "fp32_pipe_frac": 3.5 * elems / (k_ms * 1e-3) / fp32_peak})
 
@@ -626,7 +636,7 @@ def run_ours(args):
                     "api": "KernelShap._explainer.get_explanation -> dks_explain_host (pinned host X in, host phi out); N > 1: "
                            "DistributedExplainer under torchrun (phi stays on the device through the all-gather, one D2H)",
                     "timing": f"median of 5 blocks of {args.steps} calls, wall clock, max over ranks"},
-            "gpu_launches": int(launches), "roofline": roofline}
+            "gpu_launches": int(launches), "step_ms_rank0": step_spread, "roofline": roofline}
     if sustained is not None:
         line["sustained"] = sustained
     if other is not None:

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
 
         // ---- the turn-around: lane = instance of the batch, loop over the warp's 32 rows
         auto flush = [&](int bstart, int bcount) {
+            int fin_i = -1;                 // instance this lane finished in this flush (its phi is complete in local memory)
             if (lane < bcount) {
                 double beta[KPAD];
 #pragma unroll
@@ -185,19 +186,32 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
                         double val = from_fix(__ldcg(acc + k)) - delta * p.dvec[k];
                         sum += val;
                         if (fabs(val) < 1e-10) val = 0.0;
-                        const double neg = (val == 0.0) ? 0.0 : -val;
                         phi1[k] = val;
-                        phi0[k] = neg;
-                        for (int r = 0; r < p.npeers; ++r) { p.peer_phi[r][slab + (size_t)i * G + k] = val; p.peer_phi[r][(size_t)i * G + k] = neg; }
+                        phi0[k] = (val == 0.0) ? 0.0 : -val;
                         acc[k] = 0;
                     }
                     double last = delta - sum;                  // the eliminated (last) group takes the remainder
                     if (fabs(last) < 1e-10) last = 0.0;
-                    const double nlast = (last == 0.0) ? 0.0 : -last;
                     phi1[nA] = last;
-                    phi0[nA] = nlast;
-                    for (int r = 0; r < p.npeers; ++r) { p.peer_phi[r][slab + (size_t)i * G + nA] = last; p.peer_phi[r][(size_t)i * G + nA] = nlast; }
+                    phi0[nA] = (last == 0.0) ? 0.0 : -last;
                     p.done[i] = 0;
+                    fin_i = i;
+                }
+            }
+            if (p.npeers > 0) {
+                // multi-GPU: the finished instances' phi rows go to every peer's gathered buffer, stored by the whole warp
+                // (lanes = groups: coalesced NVLink packets instead of one 8-byte store per value from the finishing lane)
+                unsigned fin = __ballot_sync(0xffffffffu, fin_i >= 0);
+                while (fin) {
+                    const int src = __ffs(fin) - 1;
+                    fin &= fin - 1;
+                    const int i = __shfl_sync(0xffffffffu, fin_i, src);
+                    __syncwarp();
+                    for (int idx = lane; idx < 2 * G; idx += 32) {
+                        const size_t off = (idx < G ? 0 : slab) + (size_t)i * G + (idx < G ? idx : idx - G);
+                        const double v = __ldcg(p.phi + off);
+                        for (int r = 0; r < p.npeers; ++r) p.peer_phi[r][off] = v;
+                    }
                 }
             }
         };
