@@ -1,7 +1,10 @@
 """One l1_reg='auto' call on the BASELINE configs[2] shape (64 features, bg=512, nsamples=4096) for profiling the l1 kernels."""
+import os
 import sys
 
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from distributedkernelshap_b200.datasets import dense_tabular
 from distributedkernelshap_b200.engine import GpuKernelExplainer
