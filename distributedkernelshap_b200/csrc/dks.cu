@@ -123,8 +123,11 @@ int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
     CUDA_TRY(record_ev(ctx, 0));
     int ipb = 256 / G;
     if (ipb < 1) ipb = 1;
-    size_t psm = sizeof(double) * (size_t)ipb * G * ctx->R + (size_t)ipb * G;
-    dks::prep_kernel<<<cdiv(n, ipb), 256, psm, ctx->stream>>>(
+    const bool stage = dks::prep_smem_bytes(true, ipb, G, ctx->R, ctx->D) <= (size_t)96 * 1024;
+    const size_t psm = dks::prep_smem_bytes(stage, ipb, G, ctx->R, ctx->D);
+    auto kern = stage ? dks::prep_kernel<true> : dks::prep_kernel<false>;
+    if (psm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    kern<<<cdiv(n, ipb), 256, psm, ctx->stream>>>(
         X_dev, ctx->d_W, ctx->d_b, ctx->d_bg, ctx->d_goff, ctx->d_gcols, ctx->d_colmin, ctx->d_colmax, ctx->d_colnan,
         ctx->d_linkfnull, n, ctx->N, ctx->D, G, ctx->R, ctx->C, ctx->act, ctx->kappa, ctx->link, ipb, ctx->d_XW,
         ctx->d_vmask, ctx->d_M, ctx->d_dlink, ctx->d_hist, ctx->d_counts, ctx->d_idx_full, ctx->d_idx_other,
@@ -288,11 +291,20 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         fp.count = ctx->d_counts; fp.pmat64 = pg.pmat64; fp.dvec = pg.dvec64; fp.dlink = ctx->d_dlink;
         fp.linkfnull = ctx->d_linkfnull; fp.fnull = ctx->d_fnull; fp.acc = ctx->d_acc; fp.done = ctx->d_done; fp.phi = phi_dev;
         if (ctx->peer_world > 1 && ctx->push_in_kernel) {
+            double* slabs[16];
+            int np = 0;
             for (int r = 0; r < ctx->peer_world; ++r) {
                 double* slab = ctx->peer_base[r] + (long long)ctx->peer_rank * ctx->peer_slab;
                 if (slab == phi_dev) continue;               // phi is written in place into the local slab
-                fp.peer_phi[fp.npeers++] = slab;
+                slabs[np++] = slab;
             }
+            if (!ctx->d_peer_list) TRY(dev_alloc(&ctx->d_peer_list, (size_t)16));
+            if (ctx->peer_list_for != phi_dev) {             // (never during a capture: the graph key holds the phi pointer)
+                CUDA_TRY(cudaMemcpy(ctx->d_peer_list, slabs, sizeof(double*) * np, cudaMemcpyHostToDevice));
+                ctx->peer_list_for = phi_dev;
+            }
+            fp.npeers = np;
+            fp.peer_phi = ctx->d_peer_list;
         }
         CUDA_TRY(dks::shared_path::launch_explain_fused(fp, fcfg, ctx->sm_count, ctx->stream));
         ctx->launches += 1;
@@ -511,7 +523,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_fnull); dev_free(&ctx->d_linkfnull); dev_free(&ctx->d_BWs); dev_free(&ctx->d_bases);
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
-    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom); dev_free(&ctx->d_step);
+    dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom); dev_free(&ctx->d_step); dev_free(&ctx->d_peer_list);
     dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
@@ -1130,6 +1142,7 @@ int dks_set_peers(dks_ctx* ctx, int world, int rank, const uint64_t* gathered_pt
     }
     REQUIRE((slab_doubles & 1) == 0, "dks_set_peers: slab size must be even (128-bit stores)");
     ctx->peer_world = world; ctx->peer_rank = rank; ctx->peer_slab = slab_doubles;
+    ctx->peer_list_for = nullptr;
     return DKS_OK;
 }
 

@@ -204,6 +204,8 @@ struct dks_ctx {
     double* peer_base[16] = {};                    // device pointers to each rank's [world][slab] buffer
     unsigned long long* peer_flags[16] = {};       // rank r's flag array [world] (peer-mapped); [peer_rank] is this rank's own
     bool peer_flags_set = false;
+    double** d_peer_list = nullptr;                // device copy of the peers' slab addresses for the current phi buffer
+    double* peer_list_for = nullptr;               // the phi buffer d_peer_list was built for
     unsigned long long* d_step = nullptr;          // device-side step counter of the flag exchange
     bool push_in_kernel = true;                    // the solve epilogues store phi into the peers' buffers themselves
     // tuning knobs (dks_set_option; defaults from the environment at dks_create: DKS_FUSED, DKS_FUSED_NI, ...)

@@ -41,7 +41,7 @@ struct FusedParams {
     int* done;               // [n] row groups that have delivered (zero between launches)
     double* phi;             // [C][n][G]
     int npeers;              // multi-GPU push: phi of every finished instance also goes to these buffers ([C][n][G] each)
-    double* peer_phi[FUSED_MAX_PEERS];
+    double* const* peer_phi; // [npeers] device array of the peers' slab addresses (NULL on one GPU)
 };
 
 // one 16-column chunk whose valid columns are a run-time count: nq full quads (pair sums / products), then rem < 4 raw
@@ -61,6 +61,25 @@ __device__ __forceinline__ void chunk_sums_rt(const float (&v)[16], int nq, int 
         }
         if (rem >= 2) pair_acc<false>(A, r0, r1, t1s, t0s);
         if (rem & 1) single_acc(A, rem == 1 ? r0 : r2, t1s, t0s);
+    }
+}
+
+// multi-GPU: the phi rows of the instances this warp just finished go to every peer's gathered buffer, stored by the whole warp
+// (lanes = groups: coalesced NVLink packets instead of one 8-byte store per value from the finishing lane).  Out of line so
+// that the single-GPU instantiation of the kernel does not pay registers for it.
+__device__ __noinline__ void peer_push_finished(const double* __restrict__ phi, double* const* __restrict__ peers, int npeers,
+                                                int fin_i, int lane, int G, size_t slab) {
+    unsigned fin = __ballot_sync(0xffffffffu, fin_i >= 0);
+    while (fin) {
+        const int src = __ffs(fin) - 1;
+        fin &= fin - 1;
+        const int i = __shfl_sync(0xffffffffu, fin_i, src);
+        __syncwarp();
+        for (int idx = lane; idx < 2 * G; idx += 32) {
+            const size_t off = (idx < G ? 0 : slab) + (size_t)i * G + (idx < G ? idx : idx - G);
+            const double v = __ldcg(phi + off);
+            for (int r = 0; r < npeers; ++r) peers[r][off] = v;
+        }
     }
 }
 
@@ -198,22 +217,7 @@ __global__ void __launch_bounds__(32 * NWARPS, 1) explain_shared_fused_kernel(Fu
                     fin_i = i;
                 }
             }
-            if (p.npeers > 0) {
-                // multi-GPU: the finished instances' phi rows go to every peer's gathered buffer, stored by the whole warp
-                // (lanes = groups: coalesced NVLink packets instead of one 8-byte store per value from the finishing lane)
-                unsigned fin = __ballot_sync(0xffffffffu, fin_i >= 0);
-                while (fin) {
-                    const int src = __ffs(fin) - 1;
-                    fin &= fin - 1;
-                    const int i = __shfl_sync(0xffffffffu, fin_i, src);
-                    __syncwarp();
-                    for (int idx = lane; idx < 2 * G; idx += 32) {
-                        const size_t off = (idx < G ? 0 : slab) + (size_t)i * G + (idx < G ? idx : idx - G);
-                        const double v = __ldcg(p.phi + off);
-                        for (int r = 0; r < p.npeers; ++r) p.peer_phi[r][off] = v;
-                    }
-                }
-            }
+            if (p.npeers > 0) peer_push_finished(p.phi, p.peer_phi, p.npeers, fin_i, lane, G, slab);     // multi-GPU only (kept out of line: no registers here)
         };
 
         // a(i, s) = sum over the row's nibbles of one table entry each; the entries of the NEXT instance are loaded one
