@@ -350,16 +350,21 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
                 dks::l1::l1_moments_kernel<2><<<mgrid, dks::l1::MOM_THREADS, msm, ctx->stream>>>(lp);
             }
             const size_t per_warp = dks::l1::lars_smem_per_warp(G);
-            int wpc = (int)(((size_t)ctx->max_smem_optin - 2048) / per_warp);
+            const size_t gram_bytes = sizeof(double) * (size_t)G * G;
+            const size_t budget = (size_t)ctx->max_smem_optin - 2048;
+            // the Gram matrix of the path goes to shared memory when at least four warps still fit next to it
+            const int stage_gram = (gram_bytes + 4 * per_warp <= budget) ? 1 : 0;
+            int wpc = (int)((budget - (stage_gram ? gram_bytes : 0)) / per_warp);
             if (wpc < 1) return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection: the %d x %d Cholesky factor does not fit shared memory", G, G);
             if (wpc > 8) wpc = 8;
-            int per_sm = (int)((size_t)ctx->max_smem_optin / (per_warp * wpc + 1024));
+            const size_t lsm = per_warp * wpc + (stage_gram ? gram_bytes : 0);
+            int per_sm = (int)((size_t)ctx->max_smem_optin / (lsm + 1024));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 4) per_sm = 4;
             int lgrid = (n + wpc - 1) / wpc;
             if (lgrid > ctx->sm_count * per_sm) lgrid = ctx->sm_count * per_sm;
-            CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_lars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpc)));
-            dks::l1::l1_lars_kernel<<<lgrid, 32 * wpc, per_warp * wpc, ctx->stream>>>(lp, wpc);
+            CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_lars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            dks::l1::l1_lars_kernel<<<lgrid, 32 * wpc, lsm, ctx->stream>>>(lp, wpc, stage_gram);
         } else if (pg.pmat != nullptr) {
             dks::shared_path::WlsPmatParams pp;
             pp.n = n; pp.N = ctx->N; pp.G = G; pp.C = ctx->C; pp.S = S; pp.S_pad = S_pad; pp.link = ctx->link; pp.uniform_w = 1;

@@ -221,9 +221,10 @@ __device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
 // contribution XW[i][g][r] and the "group varies" flag (KernelExplainer.varying_groups); phase 2, one thread per
 // instance: varying bit-mask, M, histogram of M, f(x), link(f(x)) - link(fnull).
 // STAGE: the block first copies what phase 1 reads -- its instances' rows of X, W, the column statistics and the group
-// tables -- into shared memory with coalesced loads, so the per-(instance, group) loop runs without dependent global loads
-// (cold after the L2 flush of a bench step, the unstaged loop paid one DRAM round trip per column of the widest group:
-// 13.8 us per launch on the Adult shape).  The host picks STAGE when the tables fit shared memory.
+// tables -- into shared memory with coalesced loads, so the per-(instance, group) loop runs without dependent global loads.
+// (Measured on the Adult shape: 13.3 us per launch under ncu against 13.8 us unstaged -- the kernel is bound by launch +
+// one cold DRAM round trip + the serial per-instance tail, not by the column loop; kept because it is never slower.)
+// The host picks STAGE when the tables fit shared memory.
 template <bool STAGE>
 __global__ void prep_kernel(const double* __restrict__ X, const double* __restrict__ W, const double* __restrict__ b,
                             const double* __restrict__ bg, const int32_t* __restrict__ goff,

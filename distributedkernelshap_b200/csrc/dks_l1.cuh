@@ -177,12 +177,20 @@ __host__ __device__ inline size_t lars_smem_per_warp(int M) {
 }
 
 // one warp per instance
-__global__ void l1_lars_kernel(Params p, int warps_per_cta) {
+__global__ void l1_lars_kernel(Params p, int warps_per_cta, int stage_gram) {
     extern __shared__ __align__(16) unsigned char l1_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int M = p.G, C = p.C;
     const int cnt = *p.count;
     const size_t per_warp = lars_smem_per_warp(M);
+    const bool lasso_mode = p.mode != MODE_NUM_FEATURES;
+    if (stage_gram) {
+        // the Gram matrix of the path (read k (M - k) times per step) shared by the warps of the CTA, behind their private areas
+        double* sg = reinterpret_cast<double*>(l1_smem + (size_t)warps_per_cta * per_warp);
+        const double* src = lasso_mode ? p.t.gram_norm : p.t.gram_raw;
+        for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) sg[idx] = src[idx];
+        __syncthreads();
+    }
     double* L = reinterpret_cast<double*>(l1_smem + (size_t)wib * per_warp);    // packed lower triangle
     double* cov = L + (size_t)M * (M + 1) / 2;      // by variable
     double* cov0 = cov + M;
@@ -193,8 +201,9 @@ __global__ void l1_lars_kernel(Params p, int warps_per_cta) {
     double* xrow = sgn + M;                         // scratch
     double* cm = xrow + M;                          // c moments (by variable)
     int* perm = reinterpret_cast<int*>(cm + M);     // position -> variable
-    const bool lasso = p.mode != MODE_NUM_FEATURES;
-    const double* gram = lasso ? p.t.gram_norm : p.t.gram_raw;
+    const bool lasso = lasso_mode;
+    const double* gram = stage_gram ? reinterpret_cast<const double*>(l1_smem + (size_t)warps_per_cta * per_warp)
+                                    : (lasso ? p.t.gram_norm : p.t.gram_raw);
     const double nsamp = (double)p.t.n_aug;
     const int max_iter = lasso ? 500 : p.kfeat;
     const size_t slab = (size_t)p.n * M;
@@ -219,6 +228,7 @@ __global__ void l1_lars_kernel(Params p, int warps_per_cta) {
         const double K = p.mode == MODE_BIC ? log(nsamp) : 2.0;
         double best_crit = nsamp * (yy / nsamp) / (yy / nsamp + EPS64);       // path step 0: all coefficients zero
         unsigned long long best_lo = 0ull, best_hi = 0ull;
+        double rss = yy;                         // residual sum of squares along the path (centred y at step 0)
 
         while (true) {
             // most correlated inactive variable, first maximum in position order
@@ -327,26 +337,24 @@ __global__ void l1_lars_kernel(Params p, int warps_per_cta) {
             for (int pos = k + lane; pos < M; pos += 32) cov[perm[pos]] -= gamma * corr[perm[pos]];
             __syncwarp();
             if (lasso) {
-                // information criterion of this path step: RSS = y'y - 2 b'X'y + b'Gb over the active block
-                double part = 0.0;
+                // information criterion of this path step.  The residual moves along the unit equiangular vector u by gamma
+                // and r'u = C / AA (every active variable has correlation +-C with r), so
+                //     RSS_new = RSS - 2 gamma C / AA + gamma^2
+                // -- O(1) per step instead of the quadratic form b'Gb (which re-read k^2 Gram entries through L2).
+                rss += gamma * gamma - 2.0 * gamma * Cabs / AA;
                 int df = 0;
                 unsigned long long nz_lo = 0ull, nz_hi = 0ull;
                 for (int a = lane; a < k; a += 32) {
                     const int va = perm[a];
-                    double t = 0.0;
-                    for (int b2 = 0; b2 < k; ++b2) t += gram[(size_t)va * M + perm[b2]] * coef[perm[b2]];
-                    part += coef[va] * (t - 2.0 * cov0[va]);
                     if (fabs(coef[va]) > EPS64) ++df;
                     if (coef[va] != 0.0) { if (va < 64) nz_lo |= 1ull << va; else nz_hi |= 1ull << (va - 64); }
                 }
-                part = wsum(part);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     df += __shfl_xor_sync(0xffffffffu, df, o);
                     nz_lo |= __shfl_xor_sync(0xffffffffu, nz_lo, o);
                     nz_hi |= __shfl_xor_sync(0xffffffffu, nz_hi, o);
                 }
-                const double rss = yy + part;
                 const double crit = nsamp * (rss / nsamp) / (yy / nsamp + EPS64) + K * (double)df;
                 if (crit < best_crit) { best_crit = crit; best_lo = nz_lo; best_hi = nz_hi; }
             }
