@@ -252,3 +252,29 @@ def test_loaders_fall_back_to_synthetic_adult(tmp_path, monkeypatch):
     assert data["all"]["X"]["processed"]["test"].shape == (2560, 49) and data["background"]["X"]["preprocessed"].shape == (100, 49)
     assert len(data["all"]["groups"]) == 12 and sum(len(g) for g in data["all"]["groups"]) == 49
     assert clf.predict_proba(data["all"]["X"]["processed"]["test"].toarray()[:3]).shape == (3, 2)
+
+
+def test_device_summary_host_side_helpers():
+    """category_segments / importances_from_device: the host half of the device-side build_explanation post-processing."""
+    from distributedkernelshap_b200.explainers.kernel_shap import category_segments, importances_from_device
+    np.testing.assert_array_equal(category_segments(12, [2, 7], [3, 4]), [0, 1, 2, 5, 6, 7, 11, 12])
+    np.testing.assert_array_equal(category_segments(5, [0], [5]), [0, 5])
+    vals = np.arange(24, dtype=float).reshape(2, 12)
+    seg = category_segments(12, [2, 7], [3, 4])
+    np.testing.assert_array_equal(np.add.reduceat(vals, seg[:-1], axis=1), sum_categories(vals, [2, 7], [3, 4]))
+    sv = [np.array([[1.0, -3.0, 0.5], [1.0, 1.0, -0.5]]), np.array([[-1.0, 3.0, 2.5], [-1.0, -1.0, 0.5]])]
+    per = [np.abs(v).mean(0) for v in sv]
+    mean_abs = np.stack(per + [per[0] + per[1]])
+    order = np.stack([np.argsort(m, kind="stable")[::-1] for m in mean_abs]).astype(np.int32)
+    got = importances_from_device({"mean_abs": mean_abs, "order": order}, ["a", "b", "c"])
+    want = rank_by_importance(sv, ["a", "b", "c"])
+    for key in want:
+        assert got[key]["names"] == want[key]["names"]
+        np.testing.assert_allclose(got[key]["ranked_effect"], want[key]["ranked_effect"])
+    assert importances_from_device({"mean_abs": mean_abs, "order": order}, ["a"])["0"]["names"][0].startswith("feature_")
+
+
+def test_bench_sizes_the_reference_pool_by_the_cpu_quota():
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= (bench.os.cpu_count() or 1)

@@ -98,3 +98,45 @@ def test_device_plan_fixture_is_reproduced_by_the_twin():
         np.testing.assert_array_equal(plan.zbits, fx[f"zbits{k}"])
         k += 1
     assert k == 5
+
+
+def test_l1_tables_reproduce_the_augmented_system():
+    """plan.l1_tables: the per-plan Gram matrices / column statistics of upstream's augmented regression, and the moment
+    identities the device kernels rely on (csrc/dks_l1.cuh), against the explicit 2S x M system."""
+    from distributedkernelshap_b200.plan import l1_tables
+    from oracle.sklearn_lars_restated import preprocess
+    for M, S, seed in [(16, 400, 1), (70, 600, 2)]:
+        np.random.seed(seed)
+        plan = build_plan(M, S)
+        t = l1_tables(plan)
+        Z = plan.dense().astype(float)
+        w = plan.weights
+        rng = np.random.default_rng(seed)
+        y, delta = rng.standard_normal(plan.S), 0.7
+        s = Z.sum(1)
+        sq = np.sqrt(np.hstack((w * (M - s), w * s)))
+        X = (sq * np.vstack((Z, Z - 1)).T).T
+        ya = np.hstack((y, y - delta)) * sq
+        Xn, yc, _, _, xs = preprocess(X, ya)
+        np.testing.assert_allclose(t["gram_raw"], X.T @ X, atol=1e-12)
+        np.testing.assert_allclose(t["gram_norm"], Xn.T @ Xn, atol=1e-12)
+        np.testing.assert_allclose(t["scale"], xs, atol=1e-13)
+        c, u = Z.T @ (w * y), Z.T @ (t["b"] * y)
+        T1, Qw, R = (t["b"] * y).sum(), (w * y * y).sum(), ((t["sqa"] + t["sqb"]) * y).sum()
+        xty = (M * c - u) - ((T1 - u) - delta * (t["sum_b"] - t["bz"]))
+        np.testing.assert_allclose(xty, X.T @ ya, atol=1e-12)
+        ybar = (R - delta * t["sum_sqb"]) / t["n_aug"]
+        np.testing.assert_allclose((xty - t["colsum"] * ybar) / t["scale"], Xn.T @ yc, atol=1e-12)
+        yy = M * Qw - 2 * delta * T1 + delta ** 2 * t["sum_b"] - t["n_aug"] * ybar ** 2
+        assert abs(yy - yc @ yc) < 1e-11
+        # the restricted WLS of the selected features comes from the w-weighted Gram of the plain rows
+        sel = [1, 4, 7, M - 1]
+        L = sel[-1]
+        E = Z[:, sel[:-1]] - Z[:, [L]]
+        A = E.T @ (w[:, None] * E)
+        gw = t["gram_w"]
+        A2 = np.array([[gw[a, b] - gw[a, L] - gw[b, L] + gw[L, L] for b in sel[:-1]] for a in sel[:-1]])
+        np.testing.assert_allclose(A2, A, atol=1e-13)
+        rhs = E.T @ (w * (y - Z[:, L] * delta))
+        rhs2 = np.array([(c[a] - c[L]) - delta * (gw[a, L] - gw[L, L]) for a in sel[:-1]])
+        np.testing.assert_allclose(rhs2, rhs, atol=1e-13)
