@@ -431,16 +431,19 @@ def run_ours(args):
     gather, collective = None, "none"
     if world > 1:
         collective = "nccl all_gather_into_tensor"
-        # the solve epilogue stores every finished instance's phi into all peers' gathered buffers over NVLink peer memory
-        # and the explain call ends with the engine's own flag exchange (signal + wait per peer); DKS_BENCH_NCCL=1 forces
-        # ncclAllGather instead, DKS_BENCH_SYMM_BARRIER=1 the symmetric-memory barrier instead of the flags.
+        # after the solve the engine's push kernel stores this rank's phi block into all peers' gathered buffers over NVLink peer
+        # memory (128-bit coalesced stores) and the explain call ends with the engine's own flag exchange (signal + wait per
+        # peer).  Measured on an 8-GPU box (profiles/r2_bench_8gpu_d_*): 0.185 ms/step at N=8 against 0.200 with
+        # ncclAllGather and 0.210 with the stores issued from the fused kernel's epilogue (DKS_PUSH_IN_KERNEL=1).
+        # DKS_BENCH_NCCL=1 forces NCCL, DKS_BENCH_SYMM_BARRIER=1 the symmetric-memory barrier instead of the flags.
         use_push = os.environ.get("DKS_BENCH_NCCL", "0") != "1"
         if use_push:
             try:
                 own_sync = os.environ.get("DKS_BENCH_SYMM_BARRIER", "0") != "1"
                 gather = parallel.PeerGather(engine, C, n, G, torch.device("cuda", local_rank), own_sync=own_sync)
                 phi_dev = gather.local
-                collective = ("phi stored into every peer's gathered buffer by the solve epilogue (NVLink peer memory) + " +
+                how = "the fused kernel's epilogue" if os.environ.get("DKS_PUSH_IN_KERNEL", "0") == "1" else "the engine's push kernel"
+                collective = (f"phi stored into every peer's gathered buffer by {how} (NVLink peer memory) + " +
                               ("the engine's flag exchange" if own_sync else "symmetric-memory barrier"))
             except Exception as exc:                      # pragma: no cover - depends on the box
                 print(f"[bench] peer-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)

@@ -496,7 +496,7 @@ int dks_create(dks_ctx** out, int device) {
         ctx->opt_fused_ni = env_int("DKS_FUSED_NI", 0);
         ctx->opt_fused_warps = env_int("DKS_FUSED_WARPS", 0);
         ctx->opt_fused_B = env_int("DKS_FUSED_B", 0);
-        ctx->push_in_kernel = env_int("DKS_PUSH_IN_KERNEL", 1) != 0;
+        ctx->push_in_kernel = env_int("DKS_PUSH_IN_KERNEL", 0) != 0;
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;

@@ -189,7 +189,8 @@ int dks_set_kernel(dks_ctx* ctx, int kernel);       /* DKS_KERNEL_* */
 /* tuning knobs, all optional (defaults are the measured best): "fused" 0/1 -- link + projection solve inside the shared-plan
  * coalition kernel (default 1; 0 = separate (sum p1, sum p0) buffer + solve kernel); "fused_ni" 1/2 instances per pass over
  * a warp's rows; "fused_warps" 16/20 warps per CTA; "fused_batch" instances parked per warp before the turn-around;
- * "push_in_kernel" 0/1 -- multi-GPU: the solve epilogue stores phi into the peers' buffers itself; "graph" 0/1 (CUDA-graph
+ * "push_in_kernel" 0/1 -- multi-GPU: the fused kernel's epilogue stores phi into the peers' buffers itself instead of the
+ * separate push kernel (default 0: measured slower, it stalls the finishing warps); "graph" 0/1 (CUDA-graph
  * replay of dks_run_dev); "graph_timing" 0/1 -- keep the timing event records inside the graph (default 0: a replayed graph
  * carries no timing nodes and dks_last_timings reports an error after it). */
 int dks_set_option(dks_ctx* ctx, const char* name, int value);
