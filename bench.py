@@ -319,8 +319,14 @@ OTHER_CONFIGS = {
     "configs[2]": dict(label="synthetic dense tabular: 64 features (ungrouped), bg=512, nsamples=4096, LR (BASELINE.json "
                              "configs[2]; 16384 of its 1M instances)", kind="dense", features=64, bg=512, ns=4096),
     "configs[3] grouped": dict(label="wide one-hot, grouped reading: 64 variables x 16 levels = 1024 columns, bg=256, "
-                                     "nsamples=8192 (BASELINE.json configs[3]; 8192 of its 100k instances; the 1024-singleton "
-                                     "reading needs > 128 groups and is refused)", kind="onehot", features=1024, bg=256, ns=8192),
+                                     "nsamples=8192 (BASELINE.json configs[3]; 8192 of its 100k instances)", kind="onehot",
+                               features=1024, bg=256, ns=8192),
+    "configs[3] singleton": dict(label="wide one-hot, singleton reading: each of the 1024 one-hot columns its own group "
+                                       "(M = 1024: sixteen-word coalition rows, projection solve with a 1023 x 1023 normal "
+                                       "matrix factored once per plan on the host), uniform level probabilities, bg=256, "
+                                       "nsamples=8192 (BASELINE.json configs[3]; 2048 of its 100k instances); l1_reg=False "
+                                       "(feature selection is refused above 128 groups)", kind="onehot_singleton",
+                                 features=1024, bg=256, ns=8192, l1=False),
     "configs[4] one GPU": dict(label="synthetic: 128 features (two-word coalition rows), bg=512, nsamples=4096 (BASELINE.json "
                                      "configs[4]; 16384 instances = a slice of one GPU's share of the 10M)", kind="dense",
                                features=128, bg=512, ns=4096),
@@ -335,9 +341,9 @@ def measure_config(name, spec, flush, stream, steps=3, warmup=1):
     from distributedkernelshap_b200.data import DenseData
     from distributedkernelshap_b200.datasets import dense_tabular, wide_onehot
     from distributedkernelshap_b200.engine import GpuKernelExplainer
-    n = 8192 if spec["kind"] == "onehot" else 16384
+    n = {"dense": 16384, "onehot": 8192, "onehot_singleton": 2048}[spec["kind"]]
     wl = dense_tabular(n, spec["features"], spec["bg"], seed=0) if spec["kind"] == "dense" else \
-        wide_onehot(n, 64, 16, spec["bg"], seed=0)
+        wide_onehot(n, 64, 16, spec["bg"], seed=0, singleton_groups=spec["kind"] == "onehot_singleton")
     X = np.ascontiguousarray(wl["X_explain"])
     eng = GpuKernelExplainer(wl["predictor"].predict_proba, DenseData(wl["background"], wl["group_names"], wl["groups"]),
                              link="logit", seed=0)
@@ -362,6 +368,9 @@ def measure_config(name, spec, flush, stream, steps=3, warmup=1):
     t0 = time.perf_counter()
     eng.shap_values(X, nsamples=spec["ns"], l1_reg=False)
     out["e2e"] = {"value": n / (time.perf_counter() - t0), "unit": "instances/s", "l1_reg": False}
+    if not spec.get("l1", True):
+        eng.close()
+        return out
     n1 = 2048
     try:
         eng.shap_values(X[:64], nsamples=spec["ns"])                          # l1 tables uploaded

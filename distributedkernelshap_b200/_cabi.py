@@ -52,6 +52,7 @@ SIGNATURES = {
     "dks_set_nsamples": (C.c_int, [C.c_void_p, C.c_int]),
     "dks_effective_nsamples": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "dks_set_shared_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dks_set_plan_projection": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "dks_clear_plans": (C.c_int, [C.c_void_p]),
     "dks_has_shared_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "dks_set_l1": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

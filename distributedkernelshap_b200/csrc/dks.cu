@@ -9,6 +9,7 @@
 #include "dks_shared.cuh"
 #include "dks_fused.cuh"
 #include "dks_l1.cuh"
+#include "dks_wide.cuh"
 #include "dks_sampler.cuh"
 
 namespace {
@@ -117,8 +118,8 @@ cudaError_t record_ev(dks_ctx* ctx, int k) {
 int launch_prepare(dks_ctx* ctx, const double* X_dev, int n) {
     const int G = ctx->G;
     TRY(ensure_workspace(ctx, n));
-    // histogram, status word and list counters are adjacent: one memset
-    CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4), ctx->stream));
+    // status word, list counters and the histogram of M are adjacent: one memset
+    CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * (4 + G + 1), ctx->stream));
     if (!ctx->capturing) ctx->last_was_graph = false;
     CUDA_TRY(record_ev(ctx, 0));
     int ipb = 256 / G;
@@ -253,7 +254,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     const PlanDev& pg = ctx->h_plans[G <= DKS_MAX_GROUPS ? G : 0];
     const bool fast = (kernel == DKS_KERNEL_AUTO || kernel == DKS_KERNEL_SHARED) && ext_z == nullptr &&
                       ctx->act == DKS_ACT_BINARY_LOGISTIC && ctx->uniform_w && G >= 2 && pg.dmT != nullptr &&
-                      pg.S == dks_effective_S(G, ctx->nsamples_req);
+                      pg.S == dks_effective_S(G, ctx->nsamples_req) && (pg.W <= 2 || pg.ptw != nullptr);
     if (kernel == DKS_KERNEL_SHARED && !fast && ext_z == nullptr && pg.z != nullptr)
         return fail(DKS_ERR_UNSUPPORTED, "shared-plan fast path needs the binary-logistic head and uniform background weights");
     // the general kernel below (instances that are not on the shared-plan path) forks off here and joins at the end
@@ -274,6 +275,8 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     if (l1) {
         if (ext_z != nullptr || ctx->plan_mode == 1)
             return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection runs on shared plans only");
+        if (pg.W > 2)
+            return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection covers plans of at most 128 groups (M=%d)", G);
         if (!fast || ctx->h_l1[G].gram_raw == nullptr || ctx->h_l1[G].S != pg.S)
             return fail(DKS_ERR_UNSUPPORTED, "l1 feature selection needs the shared-plan path (binary-logistic head, uniform "
                         "background weights) and the l1 tables of the M=%d plan (dks_set_l1_tables)", G);
@@ -365,6 +368,19 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             if (lgrid > ctx->sm_count * per_sm) lgrid = ctx->sm_count * per_sm;
             CUDA_TRY(cudaFuncSetAttribute(dks::l1::l1_lars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
             dks::l1::l1_lars_kernel<<<lgrid, 32 * wpc, lsm, ctx->stream>>>(lp, wpc, stage_gram);
+        } else if (pg.W > 2) {
+            // more than 128 groups: link, float64 product with the host-supplied projection, remainder (dks_wide.cuh)
+            const size_t need_y = (size_t)n * S_pad, need_b = (size_t)n * pg.kpw;
+            if (need_y > ctx->cap_yw) { TRY(dev_alloc(&ctx->d_yw, need_y)); ctx->cap_yw = need_y; ctx->epoch++; }
+            if (need_b > ctx->cap_betaw) { TRY(dev_alloc(&ctx->d_betaw, need_b)); ctx->cap_betaw = need_b; ctx->epoch++; }
+            dks::wide::WideParams qp;
+            memset(&qp, 0, sizeof(qp));
+            qp.n = n; qp.N = ctx->N; qp.G = G; qp.C = ctx->C; qp.S = S; qp.S_pad = S_pad; qp.KP = pg.kpw; qp.link = ctx->link;
+            qp.sums = ctx->d_sums; qp.PT = pg.ptw; qp.dvec = pg.dvecw; qp.dlink = ctx->d_dlink;
+            qp.linkfnull = ctx->d_linkfnull; qp.fnull = ctx->d_fnull; qp.list = ctx->d_idx_full; qp.count = ctx->d_counts;
+            qp.y = ctx->d_yw; qp.beta = ctx->d_betaw; qp.phi = phi_dev;
+            CUDA_TRY(dks::wide::launch_wide_solve(qp, n, ctx->sm_count, ctx->stream));
+            ctx->launches += 2;                      // three launches; the common tail below counts one of them
         } else if (pg.pmat != nullptr) {
             dks::shared_path::WlsPmatParams pp;
             pp.n = n; pp.N = ctx->N; pp.G = G; pp.C = ctx->C; pp.S = S; pp.S_pad = S_pad; pp.link = ctx->link; pp.uniform_w = 1;
@@ -405,7 +421,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
     }
     if (G > 64) {
         // two-word coalition rows exist on the shared-plan path only: anything left over is reported, not computed
-        if (pg.z == nullptr || pg.S != dks_effective_S(G, ctx->nsamples_req)) {
+        if (pg.z == nullptr || pg.S != dks_effective_S(G, ctx->nsamples_req) || (pg.W > 2 && pg.ptw == nullptr)) {
             ctx->h_status[0] = DKS_ERR_PLAN_MISSING; ctx->h_status[1] = G;
             return fail(DKS_ERR_PLAN_MISSING, "no shared plan for M=%d at the current nsamples", G);
         }
@@ -509,10 +525,10 @@ int dks_create(dks_ctx** out, int device) {
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc((void**)&ctx->d_plans, sizeof(ctx->h_plans)));
     CUDA_TRY(cudaMemset(ctx->d_plans, 0, sizeof(ctx->h_plans)));
-    CUDA_TRY(cudaMalloc((void**)&ctx->d_hist, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4)));   // histogram, status, list counts
-    ctx->d_status = ctx->d_hist + (DKS_MAX_GROUPS + 1);
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_status, sizeof(int) * (4 + DKS_MAX_GROUPS + 1)));   // status, list counts, histogram
     ctx->d_counts = ctx->d_status + 2;
-    CUDA_TRY(cudaMemset(ctx->d_hist, 0, sizeof(int) * (DKS_MAX_GROUPS + 1 + 4)));
+    ctx->d_hist = ctx->d_status + 4;
+    CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int) * (4 + DKS_MAX_GROUPS + 1)));
     *out = ctx;
     return DKS_OK;
 }
@@ -529,7 +545,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom); dev_free(&ctx->d_step); dev_free(&ctx->d_peer_list);
-    dev_free(&ctx->d_hist); ctx->d_status = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_status); ctx->d_hist = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_yw); dev_free(&ctx->d_betaw); dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
@@ -583,8 +599,8 @@ int dks_set_groups(dks_ctx* ctx, const int32_t* group_offsets, const int32_t* gr
     BIND(ctx);
     REQUIRE(group_offsets && group_cols && G > 0, "dks_set_groups: need offsets, cols, G > 0");
     if (G > DKS_MAX_GROUPS)
-        return fail(DKS_ERR_UNSUPPORTED, "dks_set_groups: G=%d groups; this build handles at most %d (two 64-bit words of "
-                    "coalition bits per row)", G, DKS_MAX_GROUPS);
+        return fail(DKS_ERR_UNSUPPORTED, "dks_set_groups: G=%d groups; this build handles at most %d (sixteen 64-bit words "
+                    "of coalition bits per row)", G, DKS_MAX_GROUPS);
     ctx->G = G;
     ctx->h_goff.assign(group_offsets, group_offsets + G + 1);
     ctx->h_gcols.assign(group_cols, group_cols + group_offsets[G]);
@@ -766,20 +782,26 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         ctx->h_afix[M] = nullptr;
         ctx->epoch++;
     }
-    const int W = (M + 63) / 64;                            // 64-bit words per coalition row
+    const int W = dks_plan_words(M);                        // 64-bit words per coalition row
     const size_t S_even = ((size_t)S + 1) & ~(size_t)1;     // TMA bulk copies move 16-byte multiples
     CUDA_TRY(cudaMalloc((void**)&dz, sizeof(uint64_t) * S_even * W));
     CUDA_TRY(cudaMalloc((void**)&dw, sizeof(double) * S_even));
+    ctx->plan_allocs[M].push_back(dz); ctx->plan_allocs[M].push_back(dw);
     CUDA_TRY(cudaMemsetAsync(dz, 0, sizeof(uint64_t) * S_even * W, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(double) * S_even, ctx->stream));
-    CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
-    CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
-    ctx->plan_allocs[M].push_back(dz); ctx->plan_allocs[M].push_back(dw); ctx->plan_allocs[M].push_back(dc);
-    ctx->plan_allocs[M].push_back(di);
+    if (W <= 2) {
+        CUDA_TRY(cudaMalloc((void**)&dc, sizeof(double) * (M - 1) * (M - 1)));
+        ctx->plan_allocs[M].push_back(dc);
+        CUDA_TRY(cudaMalloc((void**)&di, sizeof(double) * (M - 1) * (M - 1)));
+        ctx->plan_allocs[M].push_back(di);
+    }
     CUDA_TRY(cudaMemcpyAsync(dz, zbits_host, sizeof(uint64_t) * S * W, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(dw, w_host, sizeof(double) * S, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int) * 2, ctx->stream));
-    if (W == 1) {
+    if (W > 2) {
+        // more than 128 groups: the (M-1) x (M-1) normal matrix is factored by the host, which hands the projection over
+        // with dks_set_plan_projection (the plan is not usable before)
+    } else if (W == 1) {
         size_t smem = 2 * sizeof(double) * (size_t)(M - 1) * (M - 1);
         CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dks::plan_factor_kernel<<<1, 256, smem, ctx->stream>>>(dz, dw, S, M, dc, di, ctx->d_status);
@@ -791,7 +813,7 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
         CUDA_TRY(cudaFuncSetAttribute(dks::plan_factor_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dks::plan_factor_wide_kernel<<<1, 1024, smem, ctx->stream>>>(dz, dw, S, M, dc, di, scratch, ctx->d_status);
     }
-    ctx->launches += 1;
+    if (W <= 2) ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -873,7 +895,35 @@ int dks_clear_plans(dks_ctx* ctx) {
 
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present) {
     REQUIRE(ctx && present && M >= 0 && M <= DKS_MAX_GROUPS, "dks_has_shared_plan: bad arguments");
-    *present = (ctx->h_plans[M].z != nullptr && ctx->h_plans[M].S == dks_effective_S(M, ctx->nsamples_req)) ? 1 : 0;
+    const PlanDev& pd = ctx->h_plans[M];
+    *present = (pd.z != nullptr && pd.S == dks_effective_S(M, ctx->nsamples_req) && (pd.W <= 2 || pd.ptw != nullptr)) ? 1 : 0;
+    return DKS_OK;
+}
+
+int dks_set_plan_projection(dks_ctx* ctx, int M, const double* pt_host, const double* dvec_host) {
+    BIND(ctx);
+    REQUIRE(M > 128 && M <= DKS_MAX_GROUPS, "dks_set_plan_projection: for plans of 129..%d groups (got M=%d); narrower plans "
+            "are factored on the device", DKS_MAX_GROUPS, M);
+    REQUIRE(pt_host && dvec_host, "dks_set_plan_projection: NULL table");
+    PlanDev& pd = ctx->h_plans[M];
+    REQUIRE(pd.z != nullptr && pd.W > 2, "dks_set_plan_projection: set the shared plan of M=%d first", M);
+    REQUIRE(pd.ptw == nullptr, "dks_set_plan_projection: the M=%d plan already has its projection (replace the plan first)", M);
+    const int nA = M - 1, kp = dks::wide::kpad(M);
+    double* pt = nullptr; double* dv = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&pt, sizeof(double) * (size_t)pd.S_pad * kp));
+    ctx->plan_allocs[M].push_back(pt);
+    CUDA_TRY(cudaMalloc((void**)&dv, sizeof(double) * kp));
+    ctx->plan_allocs[M].push_back(dv);
+    CUDA_TRY(cudaMemsetAsync(pt, 0, sizeof(double) * (size_t)pd.S_pad * kp, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dv, 0, sizeof(double) * kp, ctx->stream));
+    // host [S][M-1] -> device [S_pad][kp] (zero padded rows and columns)
+    CUDA_TRY(cudaMemcpy2DAsync(pt, sizeof(double) * kp, pt_host, sizeof(double) * nA, sizeof(double) * nA, (size_t)pd.S,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dv, dvec_host, sizeof(double) * nA, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    pd.ptw = pt; pd.dvecw = dv; pd.kpw = kp;
+    ctx->epoch++;
+    CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
     return DKS_OK;
 }
 
@@ -993,10 +1043,8 @@ int dks_prepare_host(dks_ctx* ctx, const double* X_host, int n) {
 int dks_get_m_histogram(dks_ctx* ctx, int32_t* hist_host) {
     BIND(ctx);
     REQUIRE(ctx->prepared && hist_host, "dks_get_m_histogram: call dks_prepare_* first");
-    int tmp[DKS_MAX_GROUPS + 1];
-    CUDA_TRY(cudaMemcpyAsync(tmp, ctx->d_hist, sizeof(tmp), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hist_host, ctx->d_hist, sizeof(int) * (ctx->G + 1), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    for (int m = 0; m <= ctx->G; ++m) hist_host[m] = tmp[m];
     return DKS_OK;
 }
 

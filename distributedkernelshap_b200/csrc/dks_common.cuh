@@ -9,11 +9,16 @@
 
 #include "dks.h"
 
-#define DKS_MAX_GROUPS 128  // coalition rows: one 64-bit word up to 64 groups, two words up to 128 (shared-plan path only)
+#define DKS_MAX_GROUPS 1024 // coalition rows: one 64-bit word up to 64 groups; two words up to 128 and sixteen up to 1024 on
+                            // the shared-plan path only
+#define DKS_MAX_OUT 128     // model outputs a thread may hold in local arrays (R <= 8 score rows, C <= 8 outputs today)
+
+// 64-bit words per coalition row of a plan over M groups: the kernels exist for rows of 1, 2 and 16 words
+__host__ __device__ __forceinline__ int dks_plan_words(int M) { return M <= 64 ? 1 : (M <= 128 ? 2 : 16); }
 
 // ---- device-visible plan table entry: one shared coalition plan per number of varying groups M ----------
 struct PlanDev {
-    const uint64_t* z;   // [S][W] coalition bits in upstream row order (W = 1 word up to 64 groups, 2 up to 128)
+    const uint64_t* z;   // [S][W] coalition bits in upstream row order (W = dks_plan_words(M))
     const double* w;     // [S] kernel weights
     const double* chol;  // [(M-1) x (M-1)] lower Cholesky factor of E^T W E (row-major), NULL if not factored
     const double* ainv;  // [(M-1) x (M-1)] inverse of E^T W E (row-major), NULL if not computed
@@ -23,6 +28,9 @@ struct PlanDev {
     const double* dvec;  // [(M-1)] P z_L
     const double* pmat64;  // [S_pad][kpad] float64 P, one row per coalition (fused kernel), NULL if not built
     const double* dvec64;  // [kpad] P z_L with the float64 P
+    const double* ptw;     // [S_pad][kpw] float64 P^T supplied by the host for plans of more than 128 groups (dks_wide.cuh)
+    const double* dvecw;   // [kpw] P z_L
+    int kpw;
     int kpad;
     int S;
     int S_pad;
@@ -132,6 +140,9 @@ struct dks_ctx {
     int l1_mode = 0, l1_k = 0, l1_others_plain = 0;
     double* d_mom = nullptr;     // [n][2G + 4] per-instance moments of y
     size_t cap_mom = 0;
+    double* d_yw = nullptr;      // [n][S_pad] link-space y of the wide (more than 128 groups) solve
+    double* d_betaw = nullptr;   // [n][kpw] its coefficients before the delta term
+    size_t cap_yw = 0, cap_betaw = 0;
     // per-instance plans drawn on the device (plan_mode 1)
     int plan_mode = 0;
     uint64_t sampler_seed = 0;
@@ -159,7 +170,7 @@ struct dks_ctx {
     uint64_t* d_vmask = nullptr;
     int* d_M = nullptr;
     double* d_dlink = nullptr;
-    int* d_hist = nullptr;       // [65] histogram of M, then status[2], then list counts[2] (one allocation, one memset)
+    int* d_hist = nullptr;       // status[2], list counts[2], then the histogram of M [G + 1] (one allocation, one memset)
     int* d_status = nullptr;
     int* d_counts = nullptr;     // [0] instances on the shared fast path, [1] the others
     int* d_idx_full = nullptr;   // [n] instances whose varying set is all G groups

@@ -156,7 +156,7 @@ __device__ __forceinline__ void row_sums_packed(const float (&dm)[MAXN], float A
 }
 
 // one warp = 32 coalition rows (one per lane) x a strided subset of the instances
-// W = 64-bit words per coalition row (1: up to 64 groups, 2: up to 128)
+// W = 64-bit words per coalition row (1: up to 64 groups, 2: up to 128; the tensor-memory version below also 16: up to 1024)
 template <int NTAIL, int W>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 1) explain_shared_kernel(SharedParams p) {
     const int lane = threadIdx.x & 31;
@@ -330,16 +330,18 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
             }
         }
         tmem_st_wait();
-        uint64_t zz[W];
+        // rows of one or two words stay in registers; sixteen-word rows (more than 128 groups) are re-read per instance
+        constexpr int WR = W <= 2 ? W : 1;
+        uint64_t zz[WR];
 #pragma unroll
-        for (int w = 0; w < W; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
+        for (int w = 0; w < WR; ++w) zz[w] = s < p.S ? p.z[(size_t)s * W + w] : 0ull;
         const int ntab = (G + 3) / 4;
         const f32x2 one2 = f2_pack(1.f, 1.f), two2 = f2_pack(2.f, 2.f);
 
         // Up to 16 groups (four nibbles): the table entries of the NEXT instance are loaded one iteration ahead (the row's
         // nibbles, hence the offsets, do not depend on the instance), so neither the index load nor the table load sits
         // in front of A.  Wider problems load in place: their per-instance arithmetic is long enough to hide it.
-        const bool ahead = ntab <= 4;
+        const bool ahead = W <= 2 && ntab <= 4;
         int off[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) off[t] = t * 16 + (int)((zz[0] >> (4 * t)) & 15ull);
@@ -364,12 +366,12 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
                         if (t < ntab) nx[t] = __ldg(p.XT + (size_t)i_cur * ntab * 16 + off[t]);
                 }
                 if (m + 2 * nparts < cnt) i_nx = p.list[m + 2 * nparts];
-            } else {
+            } else if (W <= 2) {
                 i = p.list[m];
                 const double* xt = p.XT + (size_t)i * ntab * 16;
                 double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
+                for (int w = 0; w < WR; ++w) {
 #pragma unroll 4
                     for (int t = 0; t < 16 && 16 * w + t < ntab; t += 2) {
                         a0 += __ldg(xt + (16 * w + t) * 16 + (int)((zz[w] >> (4 * t)) & 15ull));
@@ -377,6 +379,31 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
                     }
                 }
                 a = a0 + a1;
+            } else {
+                // sixteen-word rows: one word (sixteen nibble tables) at a time, the word re-read from the plan (L1/L2
+                // resident: 128 B per row); four partial sums keep the float64 add chains short
+                i = p.list[m];
+                const double* xt = p.XT + (size_t)i * ntab * 16;
+                const uint64_t* zrow = p.z + (size_t)s * W;
+                const int nwords = (ntab + 15) >> 4;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int w = 0; w < nwords; ++w) {
+                    const uint64_t zw = s < p.S ? __ldg(zrow + w) : 0ull;
+                    const double* xw = xt + (size_t)w * 256;
+                    const int nt = ntab - 16 * w < 16 ? ntab - 16 * w : 16;      // tables this word addresses
+                    if (nt == 16) {
+#pragma unroll
+                        for (int t = 0; t < 16; t += 4) {
+                            a0 += __ldg(xw + t * 16 + (int)((zw >> (4 * t)) & 15ull));
+                            a1 += __ldg(xw + (t + 1) * 16 + (int)((zw >> (4 * t + 4)) & 15ull));
+                            a2 += __ldg(xw + (t + 2) * 16 + (int)((zw >> (4 * t + 8)) & 15ull));
+                            a3 += __ldg(xw + (t + 3) * 16 + (int)((zw >> (4 * t + 12)) & 15ull));
+                        }
+                    } else {
+                        for (int t = 0; t < nt; ++t) a0 += __ldg(xw + t * 16 + (int)((zw >> (4 * t)) & 15ull));
+                    }
+                }
+                a = (a0 + a1) + (a2 + a3);
             }
             a += es;
             a = fmin(fmax(a, -120.0), 120.0);
@@ -445,7 +472,7 @@ inline bool shared_dm_in_tmem() {
 }
 
 inline void launch_explain_shared_chunk(const SharedParams& p, int words, int grid, cudaStream_t stream) {
-    if (shared_dm_in_tmem()) {
+    if (shared_dm_in_tmem() || words > 2) {                  // sixteen-word rows exist for the tensor-memory kernel only
         // column stride of a warp's slice: N rounded up to 4.  Reads are whole 16-column chunks (the last one may look into
         // the next slice, which is harmless), so the last slice must leave room for a full chunk: 5 slices up to N = 100,
         // 4 up to N = 128
@@ -458,7 +485,8 @@ inline void launch_explain_shared_chunk(const SharedParams& p, int words, int gr
 #define DKS_CASE(T)                                                                                          \
     case T:                                                                                                  \
         if (words == 1) explain_shared_tmem_kernel<T, 1><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride); \
-        else explain_shared_tmem_kernel<T, 2><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride);            \
+        else if (words == 2) explain_shared_tmem_kernel<T, 2><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride); \
+        else explain_shared_tmem_kernel<T, 16><<<grid, 32 * TM_MAX_WARPS, 0, stream>>>(p, warps_used, cstride);           \
         break;
             DKS_CASE(0) DKS_CASE(1) DKS_CASE(2) DKS_CASE(3) DKS_CASE(4) DKS_CASE(5) DKS_CASE(6) DKS_CASE(7)
             DKS_CASE(8) DKS_CASE(9) DKS_CASE(10) DKS_CASE(11) DKS_CASE(12) DKS_CASE(13) DKS_CASE(14) DKS_CASE(15)

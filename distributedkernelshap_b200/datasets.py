@@ -81,16 +81,20 @@ def dense_tabular(n, n_features, n_background, seed=0, dtype=np.float64):
             "groups": [[i] for i in range(n_features)], "group_names": [f"f{i}" for i in range(n_features)]}
 
 
-def wide_onehot(n, n_blocks=64, block_width=16, n_background=256, seed=0):
-    """Config [3] of BASELINE.json (the grouped reading): ``n_blocks`` categorical variables one-hot
-    encoded without dropping a level (``n_blocks * block_width`` columns), one group per variable, 2-class LR."""
+def wide_onehot(n, n_blocks=64, block_width=16, n_background=256, seed=0, singleton_groups=False):
+    """Config [3] of BASELINE.json: ``n_blocks`` categorical variables one-hot encoded without dropping a
+    level (``n_blocks * block_width`` columns), 2-class LR.  Grouped reading (default): one group per variable, level
+    probabilities ~ Dirichlet(1).  ``singleton_groups=True`` is the other reading -- every column its own group
+    (M = D = 1024) -- with uniform level probabilities, so that every column takes both values in the background and
+    all M groups vary for every instance (with skewed levels a column that is 0 in the whole background and in x does
+    not vary, and the varying sets differ from instance to instance)."""
     rng = np.random.default_rng(seed)
     D = n_blocks * block_width
 
     def draw(rows):
         out = np.zeros((rows, D))
         for b in range(n_blocks):
-            probs = rng.dirichlet(np.ones(block_width))
+            probs = np.full(block_width, 1.0 / block_width) if singleton_groups else rng.dirichlet(np.ones(block_width))
             levels = rng.choice(block_width, size=rows, p=probs)
             out[np.arange(rows), b * block_width + levels] = 1.0
         return out
@@ -99,6 +103,11 @@ def wide_onehot(n, n_blocks=64, block_width=16, n_background=256, seed=0):
     coef = rng.normal(0.0, 0.5, size=(1, D))
     intercept = rng.normal(0.0, 1.0, size=(1,))
     predictor = LinearSoftmaxClassifier(coef, intercept, multi_class="multinomial")
-    groups = [list(range(b * block_width, (b + 1) * block_width)) for b in range(n_blocks)]
+    if singleton_groups:
+        groups = [[c] for c in range(D)]
+        names = [f"var{c // block_width}={c % block_width}" for c in range(D)]
+    else:
+        groups = [list(range(b * block_width, (b + 1) * block_width)) for b in range(n_blocks)]
+        names = [f"var{b}" for b in range(n_blocks)]
     return {"predictor": predictor, "X_explain": both[n_background:], "background": both[:n_background],
-            "groups": groups, "group_names": [f"var{b}" for b in range(n_blocks)]}
+            "groups": groups, "group_names": names}

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _cabi
 from .data import DenseData, convert_to_data, convert_to_link
-from .plan import build_plan, l1_tables, pack_dense_plan, resolve_nsamples, sampling_info
+from .plan import build_plan, l1_tables, pack_dense_plan, projection, resolve_nsamples, sampling_info
 from .predictors import extract_linear_spec
 
 logger = logging.getLogger(__name__)
@@ -171,6 +171,11 @@ class GpuKernelExplainer:
         wanting = [M for M in present if needs(M)]
         if not wanting:
             return (0, 0, 0)
+        if max(wanting) > 128:
+            raise NotImplementedError(
+                f"l1_reg={l1_reg!r} selects features among {max(wanting)} varying groups; the CUDA engine's LARS path covers at "
+                "most 128 groups -- pass l1_reg=False for the plain constrained WLS (or 'num_features(k)' on a narrower "
+                "grouping)")
         partial = [M for M in wanting if M != G]
         if partial:
             raise NotImplementedError(
@@ -230,6 +235,10 @@ class GpuKernelExplainer:
                 continue
             plan = self.shared_plan(M, nsamples)
             _cabi.check(self.lib.dks_set_shared_plan(self._ctx, M, plan.S, _cabi.ptr(plan.zbits), _cabi.ptr(plan.weights)))
+            if M > 128:
+                # sixteen-word rows: the (M-1) x (M-1) normal matrix is factored here, once per plan, in float64
+                pt, dvec = projection(plan)
+                _cabi.check(self.lib.dks_set_plan_projection(self._ctx, M, _cabi.ptr(pt), _cabi.ptr(dvec)))
             nfixed, n_full, n_paired, cdf, weight_left = sampling_info(plan)
             if len(cdf) > 32:
                 if self.plan_mode == "per_instance":
@@ -316,7 +325,7 @@ class GpuKernelExplainer:
             _cabi.check(self.lib.dks_set_row_offset(self._ctx, row_offset))
         if plans is not None:
             if G > 64:
-                raise NotImplementedError("caller-supplied per-instance plans need at most 64 groups (two-word coalition "
+                raise NotImplementedError("caller-supplied per-instance plans need at most 64 groups (multi-word coalition "
                                           "rows exist on the shared-plan path only)")
             zb, w, stride = self._pack_external_plans(plans, n, nsamples)
             if need_hist:

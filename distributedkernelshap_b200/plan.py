@@ -2,8 +2,9 @@
 
 Host-side product code (the north star keeps host code in Python).  It follows the enumeration + sampling rule
 of ``shap.KernelExplainer.explain`` (shap==0.35.0; reached from the reference at explainers/kernel_shap.py:250/253,
-see SURVEY.md App. A.4 steps 5-9) and emits each coalition as one 64-bit word (bit k = k-th varying group
-present), the layout ``dks_set_shared_plan`` / ``dks_explain_*`` consume.
+see SURVEY.md App. A.4 steps 5-9) and emits each coalition as 64-bit words (bit k = k-th varying group
+present; one word up to 64 groups, two up to 128, sixteen up to 1024), the layout ``dks_set_shared_plan`` /
+``dks_explain_*`` consume.
 
 The random part draws from a legacy ``numpy.random.RandomState`` -- or the global ``numpy.random`` module, the
 stream the reference seeds (kernel_shap.py:228, :744) -- with exactly the calls upstream makes (one vectorised
@@ -14,7 +15,7 @@ from math import comb
 
 import numpy as np
 
-MAX_GROUPS = 128          # coalition rows are one 64-bit word up to 64 varying groups, two words up to 128
+MAX_GROUPS = 1024         # coalition rows: one 64-bit word up to 64 varying groups, two up to 128, sixteen up to 1024
 
 
 def resolve_nsamples(M, nsamples="auto"):
@@ -53,13 +54,13 @@ def _combination_bits(M, size):
 
 
 def mask_words(M):
-    """64-bit words per coalition row."""
-    return (M + 63) // 64
+    """64-bit words per coalition row: the engine's kernels exist for rows of 1, 2 and 16 words (``dks_plan_words``)."""
+    return 1 if M <= 64 else 2 if M <= 128 else 16
 
 
 class CoalitionPlan:
-    """``zbits`` uint64[S] (M <= 64) or uint64[S, 2] (little-endian words, 64 < M <= 128), ``weights`` float64[S] in
-    upstream row order, plus bookkeeping."""
+    """``zbits`` uint64[S] (M <= 64) or uint64[S, W] (little-endian words; W = 2 for 64 < M <= 128, 16 above), ``weights``
+    float64[S] in upstream row order, plus bookkeeping."""
 
     def __init__(self, M, zbits, weights, nfixed, num_full_subsets, weight_left):
         self.M = M
@@ -167,7 +168,7 @@ def build_plan(M, nsamples="auto", rng=None):
 
 
 def _build_plan_wide(M, nsamples, rng):
-    """Same rule for 64 < M <= 128, with Python integers as masks (two 64-bit words per row on the way out)."""
+    """Same rule for M > 64, with Python integers as masks (``mask_words(M)`` 64-bit words per row on the way out)."""
     from itertools import combinations
     S, _ = resolve_nsamples(M, nsamples)
     full_mask = (1 << M) - 1
@@ -229,12 +230,13 @@ def _build_plan_wide(M, nsamples, rng):
         wts = np.array(weights)
         wts[nfixed:] *= weight_left / wts[nfixed:].sum()
         weights = list(wts)
-    zbits = np.zeros((S, 2), dtype=np.uint64)
+    W = mask_words(M)
+    zbits = np.zeros((S, W), dtype=np.uint64)
     wout = np.zeros(S)
     lo64 = (1 << 64) - 1
     for r, word in enumerate(rows):
-        zbits[r, 0] = word & lo64
-        zbits[r, 1] = word >> 64
+        for q in range((M + 63) // 64):
+            zbits[r, q] = (word >> (64 * q)) & lo64
     wout[:len(weights)] = weights
     return CoalitionPlan(M, zbits, wout, nfixed, n_full, weight_left)
 
@@ -258,19 +260,35 @@ def sampling_info(plan):
 
 
 def pack_dense_plan(Z):
-    """[S, M] 0/1 matrix -> uint64[S] bit words, or uint64[S, 2] for 64 < M <= 128 (for feeding externally built plans
-    to the engine and for comparing plans in tests)."""
+    """[S, M] 0/1 matrix -> uint64[S] bit words, or uint64[S, mask_words(M)] for M > 64 (for feeding externally built
+    plans to the engine and for comparing plans in tests)."""
     Z = np.asarray(Z)
     S, M = Z.shape
     if M > MAX_GROUPS:
         raise ValueError(f"at most {MAX_GROUPS} varying groups per coalition row")
-    k = np.arange(min(M, 64), dtype=np.uint64)
-    lo = (Z[:, :64].astype(np.uint64) << k[None, :]).sum(axis=1, dtype=np.uint64)
-    if M <= 64:
-        return lo
-    k2 = np.arange(M - 64, dtype=np.uint64)
-    hi = (Z[:, 64:].astype(np.uint64) << k2[None, :]).sum(axis=1, dtype=np.uint64)
-    return np.stack([lo, hi], axis=1)
+    words = np.zeros((S, mask_words(M)), dtype=np.uint64)
+    for q in range((M + 63) // 64):
+        blk = Z[:, 64 * q:64 * q + 64].astype(np.uint64)
+        k = np.arange(blk.shape[1], dtype=np.uint64)
+        words[:, q] = (blk << k[None, :]).sum(axis=1, dtype=np.uint64)
+    return words[:, 0] if M <= 64 else words
+
+
+def projection(plan):
+    """Projection form of upstream's constrained WLS for a shared plan (``KernelExplainer.solve`` without the l1 branch):
+    with the last group eliminated, ``E = Z[:, :M-1] - Z[:, M-1:]``, ``A = E^T diag(w) E`` and
+    ``beta = inv(A) E^T diag(w) (y - z_L delta) = P y - delta d``.  Returns ``(PT [S, M-1], d [M-1])`` in float64 with
+    ``PT = P^T`` (one row per coalition) and ``d = P z_L``.  Plans of up to 128 groups get their factorisation on the
+    device (``dks_set_shared_plan``); wider plans are factored here once -- ``np.linalg.inv`` like upstream -- and uploaded
+    with ``dks_set_plan_projection``."""
+    Z = plan.dense().astype(np.float64)
+    w = np.asarray(plan.weights, dtype=np.float64)
+    zl = Z[:, -1]
+    E = Z[:, :-1] - zl[:, None]
+    EW = E * w[:, None]
+    A = E.T @ EW
+    P = np.linalg.inv(A) @ EW.T
+    return np.ascontiguousarray(P.T), np.ascontiguousarray(P @ zl)
 
 
 def l1_tables(plan):

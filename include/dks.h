@@ -91,10 +91,16 @@ int dks_predict_host(dks_ctx* ctx, const double* X_host, int n, double* out_host
 int dks_set_nsamples(dks_ctx* ctx, int nsamples);
 /* S an instance with M varying groups evaluates under the current request (upstream rule). */
 int dks_effective_nsamples(dks_ctx* ctx, int M, int* S);
-/* one plan shared by every instance with M varying groups: zbits [S][W] little-endian 64-bit words, W = 1 for M <= 64 and
- * 2 for 64 < M <= 128 (bit k = k-th varying group present; two-word rows are evaluated by the shared-plan path only),
- * w [S] kernel weights, in upstream row order.  Copies to the device and factors the normal matrix. */
+/* one plan shared by every instance with M varying groups: zbits [S][W] little-endian 64-bit words, W = 1 for M <= 64,
+ * 2 for 64 < M <= 128 and 16 for 128 < M <= 1024 (bit k = k-th varying group present; multi-word rows are evaluated by the
+ * shared-plan path only), w [S] kernel weights, in upstream row order.  Copies to the device and, up to 128 groups,
+ * factors the normal matrix there. */
 int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, const double* w_host);
+/* plans of more than 128 groups: the solve of KernelExplainer.solve (reached from kernel_shap.py:250/253; ungrouped wide
+ * arrays: kernel_shap.py:581-621) in projection form, beta = P y - delta d with P = inv(E^T W E) E^T W and d = P z_L, factored
+ * by the host in float64 (np.linalg.inv like upstream).  pt_host = P^T [S][M-1] row-major, dvec_host = d [M-1].  Call after
+ * dks_set_shared_plan of the same M; the plan is reported present (dks_has_shared_plan) only with its projection. */
+int dks_set_plan_projection(dks_ctx* ctx, int M, const double* pt_host, const double* dvec_host);
 int dks_clear_plans(dks_ctx* ctx);
 int dks_has_shared_plan(dks_ctx* ctx, int M, int* present);
 

@@ -1,6 +1,6 @@
 """Oracle outputs at the FULL BASELINE.json shapes (VERDICT r1 task 1): fixtures under tests/golden/baseline/.
 
-    python tests/golden/baseline/make_golden_baseline.py [adult] [cfg2] [cfg3] [cfg4]      (default: all; 8 processes)
+    python tests/golden/baseline/make_golden_baseline.py [adult] [cfg2] [cfg3] [cfg4] [cfg3s]   (default: all; 8 processes)
 
 adult   configs[1]: all 2560 Adult-shaped instances (the bench workload), D=49, 12 groups, bg=100, nsamples=2048,
         a FRESH coalition plan per instance (what shap does): instance i's plan is the one the oracle's build_plan draws
@@ -11,6 +11,11 @@ cfg3    configs[3], grouped reading: 64 one-hot variables x 16 levels = 1024 col
 cfg4    configs[4] shape: 128 ungrouped features (two-word coalition rows), bg=512, nsamples=4096, 8 instances, ONE plan
         shared by the 8 instances (drawn after ``np.random.seed(PLAN_SEED)``): the engine evaluates two-word rows on
         its shared-plan path.
+
+cfg3s   configs[3], the other reading: every one of the 1024 one-hot columns its own group (M = D = 1024, sixteen-word
+        coalition rows, a 1023 x 1023 normal matrix), bg=256, nsamples=8192, uniform level probabilities so that all 1024
+        groups vary, 4 instances, ONE shared plan (seeded like cfg4); the masked batch goes through 256 coalitions at a
+        time (about two minutes per instance).
 
 The plans are not stored (Adult alone would be 84 MB): the GPU test regenerates them with the oracle's build_plan from the
 same seeds and checks their SHA-256 against the one stored here, then feeds them to the engine.  Inputs come from
@@ -33,6 +38,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, REPO)
 
 PLAN_SEED = 20260921
+SHARED_PLAN = ("cfg4", "cfg3s")         # one plan for all instances of the fixture (the engine's shared-plan path)
+FIXTURES = {"adult": "adult_2560_s2048", "cfg2": "cfg2_64feat_bg512_s4096", "cfg3": "cfg3_grouped_1024col_bg256_s8192",
+            "cfg4": "cfg4_128feat_bg512_s4096", "cfg3s": "cfg3_singleton_1024groups_bg256_s8192"}
 
 
 def problem(name):
@@ -46,6 +54,8 @@ def problem(name):
         return datasets.wide_onehot(n=8, n_blocks=64, block_width=16, n_background=256, seed=3), 8192, 512
     if name == "cfg4":
         return datasets.dense_tabular(n=8, n_features=128, n_background=512, seed=4), 4096, None
+    if name == "cfg3s":
+        return datasets.wide_onehot(n=4, n_blocks=64, block_width=16, n_background=256, seed=3, singleton_groups=True), 8192, 256
     raise ValueError(name)
 
 
@@ -89,7 +99,7 @@ def _work(args):
         M = len(orc.varying_groups(x))
         Ms[i - lo] = M
         if M >= 2:
-            Z, w = instance_plan(M, nsamples, i, name == "cfg4")
+            Z, w = instance_plan(M, nsamples, i, name in SHARED_PLAN)
             phi[i - lo] = orc.explain(x, plan=(Z, w), nsamples=nsamples, l1_reg=False)
             h = hashlib.sha256(pack_bits(Z).tobytes())
             h.update(w.tobytes())
@@ -115,14 +125,13 @@ def make(name, procs=8):
     for p in parts:
         for dg in p[3]:
             h.update(dg)
-    out = os.path.join(HERE, {"adult": "adult_2560_s2048", "cfg2": "cfg2_64feat_bg512_s4096",
-                              "cfg3": "cfg3_grouped_1024col_bg256_s8192", "cfg4": "cfg4_128feat_bg512_s4096"}[name] + ".npz")
+    out = os.path.join(HERE, FIXTURES[name] + ".npz")
     np.savez_compressed(out, phi=phi, M=Ms, expected_value=parts[0][4], nsamples=nsamples, plan_seed=PLAN_SEED,
-                        plans_sha256=h.hexdigest(), data_sha256=data_sha(d), shared_plan=(name == "cfg4"))
+                        plans_sha256=h.hexdigest(), data_sha256=data_sha(d), shared_plan=(name in SHARED_PLAN))
     print(f"{name}: {n} instances in {time.time() - t0:.0f} s -> {out} ({os.path.getsize(out) / 1e3:.0f} kB)")
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["adult", "cfg2", "cfg3", "cfg4"]
+    names = sys.argv[1:] or ["adult", "cfg2", "cfg3", "cfg4", "cfg3s"]
     for nm in names:
         make(nm)

@@ -26,9 +26,7 @@ ATOL_ELEM = 5e-7
 
 def _load(name):
     import make_golden_baseline as gen
-    fixtures = {"adult": "adult_2560_s2048", "cfg2": "cfg2_64feat_bg512_s4096", "cfg3": "cfg3_grouped_1024col_bg256_s8192",
-                "cfg4": "cfg4_128feat_bg512_s4096"}
-    g = np.load(os.path.join(HERE, "golden", "baseline", fixtures[name] + ".npz"))
+    g = np.load(os.path.join(HERE, "golden", "baseline", gen.FIXTURES[name] + ".npz"))
     d, nsamples, _ = gen.problem(name)
     assert gen.data_sha(d) == str(g["data_sha256"]), "datasets.py no longer generates the inputs the fixture was made from"
     assert int(g["nsamples"]) == nsamples
@@ -134,3 +132,24 @@ def test_full_shape_shared_plan_path(name):
     want = np.stack([orc.explain(d["X_explain"][i:i + 1], plan=(plan.dense(), plan.weights), nsamples=nsamples,
                                  l1_reg=False) for i in rows])
     _check([got[c][rows] for c in range(2)], want, f"{name} shared plan")
+
+
+def test_config3_singleton_reading_1024_groups_shared_plan():
+    """configs[3] read as 1024 singleton groups (M = D = 1024, S = 8192, N = 256): sixteen-word coalition rows through the
+    shared-plan coalition kernel, two background chunks of 128, and the float64 projection solve with the 1023 x 1023
+    normal matrix factored on the host (csrc/dks_wide.cuh).  The unseeded engine draws its M = 1024 plan from the state the
+    fixture's generator seeded, i.e. the very plan the oracle evaluated."""
+    gen, g, d, nsamples = _load("cfg3s")
+    assert (g["M"] == 1024).all()
+    np.random.seed(int(g["plan_seed"]))
+    eng = _engine(d)
+    got = eng.shap_values(d["X_explain"], nsamples=nsamples, l1_reg=False)
+    np.random.seed(int(g["plan_seed"]))
+    from distributedkernelshap_b200.plan import build_plan
+    p = build_plan(1024, nsamples)
+    Z, w = gen.instance_plan(1024, nsamples, 0, True)
+    np.testing.assert_array_equal(p.dense(), Z)             # product plan builder == oracle's, bit for bit
+    np.testing.assert_array_equal(p.weights, w)
+    np.testing.assert_allclose(eng.expected_value, g["expected_value"], rtol=1e-12)
+    _check(got, g["phi"], "cfg3 singleton shared plan")
+    np.testing.assert_allclose(got[0], -got[1], rtol=0, atol=1e-12)

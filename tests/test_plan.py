@@ -37,7 +37,7 @@ def test_plan_rejects_unsupported_sizes():
     with pytest.raises(ValueError):
         build_plan(1)
     with pytest.raises(ValueError):
-        build_plan(129)
+        build_plan(1025)
 
 
 def test_sampling_info_and_philox_stream_adapter():
@@ -78,7 +78,37 @@ def test_wide_plans_two_words_match_the_oracle():
         np.testing.assert_array_equal(plan.dense(), Z)
         np.testing.assert_allclose(plan.weights, w, rtol=1e-14)
     with pytest.raises(ValueError):
-        build_plan(129, 100)
+        build_plan(1025, 100)
+
+
+def test_plans_of_more_than_128_groups_and_their_projection():
+    """Sixteen-word rows (129..1024 groups): the product's builder reproduces the oracle's plan bit for bit, and
+    plan.projection() is the solve of upstream's constrained WLS: beta = P y - delta d equals inv(E^T W E) E^T W (y - z_L delta)
+    and the oracle's own _solve on the same (Z, w, y)."""
+    from distributedkernelshap_b200.plan import build_plan, mask_words, pack_dense_plan, projection
+    from oracle.shap_kernel_oracle import build_plan as oracle_build_plan
+    for M, ns in [(129, 600), (200, 1000), (1024, 4096)]:
+        np.random.seed(11)
+        plan = build_plan(M, ns)
+        np.random.seed(11)
+        Z, w, info = oracle_build_plan(M, plan.S)
+        assert mask_words(M) == 16 and plan.zbits.shape == (plan.S, 16)
+        np.testing.assert_array_equal(plan.dense(), Z)
+        np.testing.assert_array_equal(plan.zbits, pack_dense_plan(Z))
+        np.testing.assert_array_equal(plan.weights, w)
+        assert not plan.zbits[:, (M + 63) // 64:].any()              # unused words stay zero
+    np.random.seed(3)
+    plan = build_plan(200, 1500)
+    PT, d = projection(plan)
+    assert PT.shape == (plan.S, 199) and d.shape == (199,)
+    Zf = plan.dense().astype(np.float64)
+    rng = np.random.default_rng(0)
+    y, delta = rng.standard_normal(plan.S), 0.7
+    E = Zf[:, :-1] - Zf[:, -1:]
+    A = E.T @ (E * plan.weights[:, None])
+    want = np.linalg.inv(A) @ (E.T @ (plan.weights * (y - Zf[:, -1] * delta)))
+    got = PT.T @ y - delta * d
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
 
 
 def test_device_plan_fixture_is_reproduced_by_the_twin():
