@@ -321,6 +321,12 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
         dks::shared_path::SharedParams sp;
         sp.n = n; sp.N = ctx->N; sp.G = G; sp.S = S; sp.S_pad = S_pad; sp.scale = ctx->scale;
         sp.DmT = pg.dmT; sp.dme = pg.dme; sp.z = pg.z; sp.XT = ctx->d_XT; sp.list = ctx->d_idx_full; sp.count = ctx->d_counts; sp.sums = ctx->d_sums; sp.accumulate = 0;
+        sp.acache = nullptr; sp.acache_mode = 0;
+        if (pg.W > 2 && ctx->opt_wide_acache && ctx->N > dks::shared_path::MAXN) {
+            // sixteen-word rows, several background chunks: A(i, s) is computed by the first chunk's launch only
+            if (need > ctx->cap_acache) { TRY(dev_alloc(&ctx->d_acache, need)); ctx->cap_acache = need; ctx->epoch++; }
+            sp.acache = ctx->d_acache;
+        }
         ctx->launches += dks::shared_path::launch_explain_shared(sp, pg.W, ctx->sm_count, ctx->stream) - 1;
         dks::shared_path::WlsSharedParams wp;
         wp.n = n; wp.N = ctx->N; wp.G = G; wp.C = ctx->C; wp.S = S; wp.S_pad = S_pad; wp.link = ctx->link;
@@ -379,7 +385,7 @@ int launch_explain(dks_ctx* ctx, double* phi_dev, const uint64_t* ext_z, const d
             qp.sums = ctx->d_sums; qp.PT = pg.ptw; qp.dvec = pg.dvecw; qp.dlink = ctx->d_dlink;
             qp.linkfnull = ctx->d_linkfnull; qp.fnull = ctx->d_fnull; qp.list = ctx->d_idx_full; qp.count = ctx->d_counts;
             qp.y = ctx->d_yw; qp.beta = ctx->d_betaw; qp.phi = phi_dev;
-            CUDA_TRY(dks::wide::launch_wide_solve(qp, n, ctx->sm_count, ctx->stream));
+            CUDA_TRY(dks::wide::launch_wide_solve(qp, n, ctx->sm_count, ctx->opt_wide_gemm, ctx->stream));
             ctx->launches += 2;                      // three launches; the common tail below counts one of them
         } else if (pg.pmat != nullptr) {
             dks::shared_path::WlsPmatParams pp;
@@ -513,6 +519,8 @@ int dks_create(dks_ctx** out, int device) {
         ctx->opt_fused_warps = env_int("DKS_FUSED_WARPS", 0);
         ctx->opt_fused_B = env_int("DKS_FUSED_B", 0);
         ctx->push_in_kernel = env_int("DKS_PUSH_IN_KERNEL", 0) != 0;
+        ctx->opt_wide_gemm = env_int("DKS_WIDE_GEMM", ctx->opt_wide_gemm) == 2 ? 2 : 1;
+        ctx->opt_wide_acache = env_int("DKS_WIDE_ACACHE", ctx->opt_wide_acache ? 1 : 0) != 0;
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -545,7 +553,7 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->d_wbf); dev_free(&ctx->d_plans); dev_free(&ctx->d_X); dev_free(&ctx->d_XW); dev_free(&ctx->d_XT);
     dev_free(&ctx->d_vflag); dev_free(&ctx->d_vmask); dev_free(&ctx->d_M); dev_free(&ctx->d_dlink);
     dev_free(&ctx->d_idx_full); dev_free(&ctx->d_idx_other); dev_free(&ctx->d_sums); dev_free(&ctx->d_acc); dev_free(&ctx->d_done); dev_free(&ctx->d_mom); dev_free(&ctx->d_step); dev_free(&ctx->d_peer_list);
-    dev_free(&ctx->d_status); ctx->d_hist = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_yw); dev_free(&ctx->d_betaw); dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
+    dev_free(&ctx->d_status); ctx->d_hist = nullptr; ctx->d_counts = nullptr; dev_free(&ctx->d_yw); dev_free(&ctx->d_betaw); dev_free(&ctx->d_acache); dev_free(&ctx->d_phi); if (ctx->h_phi_pin) { cudaFreeHost(ctx->h_phi_pin); ctx->h_phi_pin = nullptr; } dev_free(&ctx->d_genz); dev_free(&ctx->d_genw); dev_free(&ctx->d_genchol); dev_free(&ctx->d_genainv); dev_free(&ctx->d_afix); dev_free(&ctx->d_sinfo); dev_free(&ctx->d_extz);
     dev_free(&ctx->d_extw);
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
@@ -1335,6 +1343,8 @@ int dks_set_option(dks_ctx* ctx, const char* name, int value) {
     else if (key == "push_in_kernel") ctx->push_in_kernel = value != 0;
     else if (key == "graph") ctx->graph_enabled = value != 0;
     else if (key == "graph_timing") ctx->opt_graph_timing = value != 0;
+    else if (key == "wide_gemm") ctx->opt_wide_gemm = value == 2 ? 2 : 1;
+    else if (key == "wide_acache") ctx->opt_wide_acache = value != 0;
     else return fail(DKS_ERR_INVALID, "dks_set_option: unknown option '%s'", name);
     ctx->epoch++;                      // a captured graph holds the old launch sequence
     return DKS_OK;

@@ -68,6 +68,8 @@ struct SharedParams {
     const int* count;        // their number (device)
     float2* sums;            // [n][S_pad] (sum p1, sum p0)
     int accumulate;          // add to sums instead of overwriting them (second and later background chunks)
+    float* acache;           // [n][S_pad] A(i, s) of sixteen-word rows, kept between the launches of the background chunks
+    int acache_mode;         // 0: off, 1: this launch writes it (first chunk), 2: this launch reads it
 };
 
 // Two sigmoids with one reciprocal.  With ua = 2^ta, ub = 2^tb:  (1+ua)(1+ub) = 1 + sm + q,  sm = ua + ub, q = ua*ub
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
         for (int m = part; m < cnt; m += nparts) {
             int i;
             double a;
+            bool cached = false;                             // only ever set for sixteen-word rows
             if (ahead) {
                 i = i_cur;
                 a = (nx[0] + nx[1]) + (nx[2] + nx[3]);
@@ -379,6 +382,12 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
                     }
                 }
                 a = a0 + a1;
+            } else if (p.acache_mode == 2) {
+                // sixteen-word rows, second and later background chunks: A(i, s) does not depend on the chunk (the row
+                // exponent dme[s] covers the whole background) -- the first chunk's launch left it in acache
+                i = p.list[m];
+                a = 0.0;
+                cached = true;
             } else {
                 // sixteen-word rows: one word (sixteen nibble tables) at a time, the word re-read from the plan (L1/L2
                 // resident: 128 B per row); four partial sums keep the float64 add chains short
@@ -405,10 +414,16 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 1) explain_shared_tmem_kern
                 }
                 a = (a0 + a1) + (a2 + a3);
             }
-            a += es;
-            a = fmin(fmax(a, -120.0), 120.0);
-            const double an = rint(a);
-            const float A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
+            float A;
+            if (W > 2 && cached) {
+                A = p.acache[(size_t)i * p.S_pad + s];
+            } else {
+                a += es;
+                a = fmin(fmax(a, -120.0), 120.0);
+                const double an = rint(a);
+                A = ex2_approx((float)(a - an)) * __int_as_float((127 + (int)an) << 23);
+                if (W > 2 && p.acache_mode == 1) p.acache[(size_t)i * p.S_pad + s] = A;
+            }
             // A^2 must stay finite in fp32 (the normalised entries are <= sqrt 2, so A bounds every u): rows beyond that
             // take the clamped scalar path on the raw row from global memory (rare: saturated scores)
             const bool risky = __any_sync(0xffffffffu, A > 1.0e18f);
@@ -513,10 +528,12 @@ inline int launch_explain_shared(SharedParams p, int words, int grid, cudaStream
     const int N = p.N;
     const float* dm = p.DmT;
     int launches = 0;
+    const bool use_cache = words > 2 && p.acache != nullptr && N > MAXN;
     for (int j0 = 0; j0 < N; j0 += MAXN, ++launches) {
         p.N = N - j0 < MAXN ? N - j0 : MAXN;
         p.DmT = dm + (size_t)j0 * p.S_pad;
         p.accumulate = j0 > 0;
+        p.acache_mode = use_cache ? (j0 == 0 ? 1 : 2) : 0;
         launch_explain_shared_chunk(p, words, grid, stream);
     }
     return launches;

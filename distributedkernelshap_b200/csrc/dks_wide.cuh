@@ -120,6 +120,80 @@ __global__ void __launch_bounds__(THREADS) wide_beta_kernel(WideParams p) {
     }
 }
 
+// Second version of the product (profiles/r2l_ncu_full_wide_path.csv showed the first one bound by shared-memory loads:
+// 2.9e8 bank conflicts, FP64 pipe 29 % active).  128 instances x 64 coefficients per CTA, 8 x 4 outputs per thread, every
+// shared-memory operand a 128-bit load: a thread's rows are 4 ty .. +3 and 64 + 4 ty .. +3 (a warp holds two values of ty:
+// broadcasts), its columns 2 tx, 2 tx + 1 and 32 + 2 tx, 32 + 2 tx + 1 (sixteen consecutive 16-byte pieces per load: no
+// conflicts).  Per coalition step 6 LDS.128 feed 32 DFMA.  Same fixed summation order as the first version: identical bits.
+constexpr int BM2 = 128;
+__global__ void __launch_bounds__(THREADS) wide_beta2_kernel(WideParams p) {
+    __shared__ __align__(16) double As[BK][BM2];     // y tile, transposed: [coalition][instance]
+    __shared__ __align__(16) double Bs[BK][BN];      // PT tile: [coalition][coefficient]
+    __shared__ int s_inst[BM2];
+    const int cnt = *p.count;
+    const int m0 = blockIdx.y * BM2, k0 = blockIdx.x * BN;
+    if (m0 >= cnt) return;
+    const int t = threadIdx.x;
+    if (t < BM2) s_inst[t] = m0 + t < cnt ? p.list[m0 + t] : -1;
+    __syncthreads();
+    // loader roles: y tile -- instance t & 127, eight consecutive coalitions from 8 (t >> 7); PT tile -- coalition t >> 4,
+    // four coefficients from 4 (t & 15)
+    const int la_m = t & (BM2 - 1), la_k = (t >> 7) * 8;
+    const int lb_k = t >> 4, lb_c = (t & 15) * 4;
+    const int inst = s_inst[la_m];
+    const double* yrow = inst >= 0 ? p.y + (size_t)inst * p.S_pad : nullptr;       // rows are 256-byte aligned (S_pad % 32 == 0)
+    const int ty = t >> 4, tx = t & 15;
+    double acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int s0 = 0; s0 < p.S_pad; s0 += BK) {
+        if (yrow) {
+            const double2* src = reinterpret_cast<const double2*>(yrow + s0 + la_k);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 v = src[q];
+                As[la_k + 2 * q][la_m] = v.x;
+                As[la_k + 2 * q + 1][la_m] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) As[la_k + q][la_m] = 0.0;
+        }
+        const double2* prow = reinterpret_cast<const double2*>(p.PT + (size_t)(s0 + lb_k) * p.KP + k0 + lb_c);   // KP % 64 == 0
+        *reinterpret_cast<double2*>(&Bs[lb_k][lb_c]) = prow[0];
+        *reinterpret_cast<double2*>(&Bs[lb_k][lb_c + 2]) = prow[1];
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const double2 a0 = *reinterpret_cast<const double2*>(&As[kk][4 * ty]);
+            const double2 a1 = *reinterpret_cast<const double2*>(&As[kk][4 * ty + 2]);
+            const double2 a2 = *reinterpret_cast<const double2*>(&As[kk][64 + 4 * ty]);
+            const double2 a3 = *reinterpret_cast<const double2*>(&As[kk][64 + 4 * ty + 2]);
+            const double2 b0 = *reinterpret_cast<const double2*>(&Bs[kk][2 * tx]);
+            const double2 b1 = *reinterpret_cast<const double2*>(&Bs[kk][32 + 2 * tx]);
+            const double a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+            const double b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = s_inst[(r < 4 ? 0 : 64) + 4 * ty + (r & 3)];
+        if (i < 0) continue;
+        double* out = p.beta + (size_t)i * p.KP + k0;
+        double2 lo, hi;
+        lo.x = acc[r][0]; lo.y = acc[r][1]; hi.x = acc[r][2]; hi.y = acc[r][3];
+        *reinterpret_cast<double2*>(out + 2 * tx) = lo;
+        *reinterpret_cast<double2*>(out + 32 + 2 * tx) = hi;
+    }
+}
+
 // one CTA per listed instance: phi_k = beta_k - delta d_k, the eliminated (last) group takes the remainder
 __global__ void __launch_bounds__(256) wide_finish_kernel(WideParams p) {
     __shared__ double s_part[8];
@@ -160,13 +234,15 @@ inline dim3 link_grid(int S_pad, int n, int sm_count) {
     return dim3(gx, n < 4 * sm_count ? n : 4 * sm_count);
 }
 inline dim3 beta_grid(int KP, int n) { return dim3(KP / BN, (n + BM - 1) / BM); }
+inline dim3 beta2_grid(int KP, int n) { return dim3(KP / BN, (n + BM2 - 1) / BM2); }
 inline int finish_grid(int n, int sm_count) { return n < 8 * sm_count ? n : 8 * sm_count; }
 
 #ifndef DKS_HOST_EMULATION
 // three launches on `stream`; n = instances of the call (upper bound of the device-side count)
-inline cudaError_t launch_wide_solve(const WideParams& p, int n, int sm_count, cudaStream_t stream) {
+inline cudaError_t launch_wide_solve(const WideParams& p, int n, int sm_count, int gemm_version, cudaStream_t stream) {
     wide_link_kernel<<<link_grid(p.S_pad, n, sm_count), 256, 0, stream>>>(p);
-    wide_beta_kernel<<<beta_grid(p.KP, n), THREADS, 0, stream>>>(p);
+    if (gemm_version == 2) wide_beta2_kernel<<<beta2_grid(p.KP, n), THREADS, 0, stream>>>(p);
+    else wide_beta_kernel<<<beta_grid(p.KP, n), THREADS, 0, stream>>>(p);
     wide_finish_kernel<<<finish_grid(n, sm_count), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }

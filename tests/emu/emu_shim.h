@@ -17,8 +17,10 @@
 #define __forceinline__ inline
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct float2 { float x, y; };
+struct alignas(16) double2 { double x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct dim3 {
     unsigned x = 1, y = 1, z = 1;

@@ -47,10 +47,18 @@ static int run_case(int n, int cnt, int G, int S, int N, int link, int sm_count,
 
     emu::launch(link_grid(S_pad, n, sm_count), dim3(256), wide_link_kernel, p);
     emu::launch(beta_grid(KP, n), dim3(THREADS), wide_beta_kernel, p);
+    // the second version of the product must give the same bits (same summation order) and leave unlisted rows alone
+    std::vector<double> beta2((size_t)n * KP, std::nan(""));
+    WideParams p2 = p;
+    p2.beta = beta2.data();
+    emu::launch(beta2_grid(KP, n), dim3(THREADS), wide_beta2_kernel, p2);
+    int beta_mismatch = 0;
+    for (size_t q = 0; q < beta.size(); ++q)
+        if (std::memcmp(&beta[q], &beta2[q], sizeof(double)) != 0) ++beta_mismatch;
     emu::launch(dim3(finish_grid(n, sm_count)), dim3(256), wide_finish_kernel, p);
 
     double ey = 0, eb = 0, ep = 0, esum = 0;
-    int bad = 0;
+    int bad = beta_mismatch;
     std::vector<char> listed(n, 0);
     for (int m = 0; m < cnt; ++m) listed[list[m]] = 1;
     for (int i = 0; i < n; ++i) {
@@ -99,6 +107,7 @@ int main() {
     rc |= run_case(70, 70, 130, 97, 256, DKS_LINK_IDENTITY, 1, 2);      // KP = 192; more instances than finish CTAs (8)
     rc |= run_case(5, 3, 1024, 64, 16, DKS_LINK_LOGIT, 148, 3);         // the configs[3] width: KP = 1024
     rc |= run_case(64, 64, 129, 33, 100, DKS_LINK_LOGIT, 1, 4);         // exactly one full tile; smallest wide M
+    rc |= run_case(300, 257, 193, 70, 30, DKS_LINK_LOGIT, 3, 5);        // three 128-instance tiles (last with one row), M - 1 = 192
     std::printf(rc ? "FAILED\n" : "OK\n");
     return rc;
 }
