@@ -23,6 +23,21 @@ MODEL_CHECK_RTOL = 1e-9
 MAX_ROWS_PER_CALL = 65536     # rows per C-ABI call: bounds the engine's per-call workspace (n x S x 8 B on the fast path)
 
 
+def refuse_partial_sets_beyond_64_groups(G, hist):
+    """Multi-word coalition rows (more than 64 groups) exist on the shared-plan path only, which takes the instances whose
+    groups ALL vary.  ``hist[M]`` = instances with M varying groups: anything below G is refused here, before plans (and,
+    beyond 128 groups, their projections) are built for sizes no kernel would evaluate -- the library reports the same
+    condition as status 3 (unsupported)."""
+    if G <= 64:
+        return
+    partial = [M for M in range(0, G) if hist[M] > 0]
+    if partial:
+        raise NotImplementedError(
+            f"{int(sum(hist[M] for M in partial))} instance(s) have a partial varying set (M in {partial[:8]}"
+            f"{'...' if len(partial) > 8 else ''} of {G} groups): more than 64 groups run on the shared-plan path, which "
+            "needs every group to vary (unsupported otherwise)")
+
+
 class GpuKernelExplainer:
     """CUDA KernelSHAP explainer with the interface of ``shap.KernelExplainer`` / ``KernelExplainerWrapper``.
 
@@ -226,6 +241,7 @@ class GpuKernelExplainer:
         return plan
 
     def _ensure_shared_plans(self, hist, nsamples):
+        refuse_partial_sets_beyond_64_groups(self.data.groups_size, hist)
         for M in range(2, self.data.groups_size + 1):
             if hist[M] == 0:
                 continue

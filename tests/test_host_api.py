@@ -278,3 +278,18 @@ def test_bench_sizes_the_reference_pool_by_the_cpu_quota():
     import bench
     n = bench.usable_cores()
     assert 1 <= n <= (bench.os.cpu_count() or 1)
+
+
+def test_partial_varying_sets_are_refused_beyond_64_groups():
+    """Multi-word coalition rows run on the shared-plan path only (every group must vary): the engine refuses the batch
+    before building plans for sizes no kernel evaluates; up to 64 groups the general kernels take partial sets."""
+    from distributedkernelshap_b200.engine import refuse_partial_sets_beyond_64_groups as refuse
+    hist = np.zeros(13, dtype=np.int32)
+    hist[[3, 12]] = 4, 9
+    refuse(12, hist)
+    hist = np.zeros(201, dtype=np.int32)
+    hist[200] = 7
+    refuse(200, hist)
+    hist[[0, 198]] = 1, 2
+    with pytest.raises(NotImplementedError, match="3 instance.*more than 64 groups.*unsupported"):
+        refuse(200, hist)
