@@ -198,7 +198,10 @@ int dks_set_kernel(dks_ctx* ctx, int kernel);       /* DKS_KERNEL_* */
  * "push_in_kernel" 0/1 -- multi-GPU: the fused kernel's epilogue stores phi into the peers' buffers itself instead of the
  * separate push kernel (default 0: measured slower, it stalls the finishing warps); "graph" 0/1 (CUDA-graph
  * replay of dks_run_dev); "graph_timing" 0/1 -- keep the timing event records inside the graph (default 0: a replayed graph
- * carries no timing nodes and dks_last_timings reports an error after it). */
+ * carries no timing nodes and dks_last_timings reports an error after it); plans of more than 128 groups: "wide_gemm" 1/2 --
+ * float64 product of the projection solve, 2 = 128 x 64 tiles with conflict-free 128-bit shared-memory operands (default),
+ * 1 = the first 64 x 64 version; "wide_acache" 0/1 -- A(i, s) of sixteen-word rows computed by the first background
+ * chunk's launch only (default 1).  Both give identical bits either way. */
 int dks_set_option(dks_ctx* ctx, const char* name, int value);
 int dks_kernel_launches(dks_ctx* ctx, int64_t* count); /* kernels launched by this ctx so far */
 /* device-time of the last explain's stages in ms (CUDA events on the ctx stream): [0] prepare, [1] fused
