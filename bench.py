@@ -333,7 +333,7 @@ OTHER_CONFIGS = {
 }
 
 
-def measure_config(name, spec, flush, stream, steps=3, warmup=1):
+def measure_config(name, spec, flush, stream, steps=3, warmup=2):
     """Throughput of one of the other BASELINE.json configs at a bounded instance count on one GPU (shared plans): device
     resident (CUDA events, L2 flushed between steps), through the host API with l1_reg=False, and through the host API with
     the reference's DEFAULT kwargs (l1_reg='auto': LassoLarsIC feature selection on the device, csrc/dks_l1.cuh)."""
@@ -353,7 +353,7 @@ def measure_config(name, spec, flush, stream, steps=3, warmup=1):
     X_dev = torch.from_numpy(X).cuda()
     phi = torch.empty((2, n, G), dtype=torch.float64, device="cuda")
     ms = []
-    for k in range(warmup + steps):
+    for k in range(warmup + steps):       # two warm-up steps: the first runs plainly, the second captures the CUDA graph
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
