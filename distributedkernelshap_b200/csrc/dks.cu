@@ -558,7 +558,6 @@ int dks_destroy(dks_ctx* ctx) {
     dev_free(&ctx->dbg_T);
     dev_free(&ctx->dbg_time);
     free_plan_allocs(ctx, -1);
-    dks::tc_release(ctx);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -722,7 +721,6 @@ int dks_fit(dks_ctx* ctx) {
         ctx->max_plan_S = 0;
         CUDA_TRY(cudaMemcpy(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice));
     }
-    TRY(dks::tc_fit(ctx));
     ctx->fitted = true;
     ctx->epoch++;
     return DKS_OK;
@@ -883,7 +881,6 @@ int dks_set_shared_plan(dks_ctx* ctx, int M, int S, const uint64_t* zbits_host, 
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plans, ctx->h_plans, sizeof(ctx->h_plans), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (S > ctx->max_plan_S) ctx->max_plan_S = S;
-    if (W == 1) TRY(dks::tc_plan_changed(ctx, M));
     return DKS_OK;
 }
 

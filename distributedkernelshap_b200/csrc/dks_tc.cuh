@@ -906,8 +906,5 @@ inline int tc_launch(dks_ctx* ctx, const ExplainParams& p, cudaStream_t stream) 
     return DKS_OK;
 }
 
-inline int tc_fit(dks_ctx*) { return DKS_OK; }
-inline int tc_plan_changed(dks_ctx*, int) { return DKS_OK; }
-inline void tc_release(dks_ctx*) {}
 
 }  // namespace dks
